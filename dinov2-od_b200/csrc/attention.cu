@@ -1,0 +1,306 @@
+// dod_fmha_fwd — fused multi-head self-attention, head dim 64, for sm_100a.
+//
+// One CTA per (batch, head, 128-query tile).  Flash-style single pass over the
+// keys in tiles of 128:
+//     S = Q.K^T           tcgen05.mma  (SS: Q, K from 128B-swizzled smem)   -> TMEM
+//     P = exp2(S*c - m)   4 softmax warps, one query row per thread (tcgen05.ld)
+//     O += P.V            tcgen05.mma  (TS: P from TMEM as bf16, V MN-major smem)
+// O stays in TMEM for the whole pass; the running max is only advanced (and O
+// rescaled through tcgen05.ld/st) when it grows by more than 2^8, so the common
+// iteration touches O not at all.  K and V are double-buffered TMA rings; the
+// S_{j+1} MMA is issued as soon as S_j has been pulled into registers so the
+// tensor pipe runs under the softmax.  Two CTAs are resident per SM (80 KB smem,
+// 256 TMEM columns each), which overlaps one CTA's softmax with the other's MMA.
+//
+// Replaces F.scaled_dot_product_attention behind HF Dinov2SelfAttention
+// (transformers modeling_dinov2.py:215-229); scale 1/sqrt(64), non-causal,
+// no mask, dropout 0.
+
+#include "common.cuh"
+#include "../../include/dod.h"
+
+namespace dod {
+void count_launch(int n = 1);
+namespace {
+
+constexpr int kD = 64;        // head dim
+constexpr int kTile = 128;    // query rows per CTA == key rows per tile
+constexpr int kTileBytes = kTile * kD * 2;  // 16 KB
+constexpr int kKVStages = 2;
+constexpr uint32_t kTmemCols = 256;
+constexpr uint32_t kColS = 0, kColP = 128, kColO = 192;
+constexpr int kSoftmaxThreads = 128;
+constexpr int kThreads = kSoftmaxThreads + 32;  // + one TMA/MMA warp
+constexpr int kSmemBytes = kTileBytes * (1 + 2 * kKVStages) + 256 + 1024;
+
+struct FmhaParams {
+  int seq, heads;
+  int q_off, k_off, v_off;
+  float scale_log2;  // scale * log2(e)
+  __nv_bfloat16* ctx;
+  int64_t ldo;
+};
+
+__global__ void __launch_bounds__(kThreads, 2)
+fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kTileBytes;
+  uint8_t* sV = sK + kKVStages * kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kKVStages * kTileBytes);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;   // [2]
+  uint64_t* k_empty = bars + 3;  // [2]
+  uint64_t* v_full = bars + 5;   // [2]
+  uint64_t* v_empty = bars + 7;  // [2]
+  uint64_t* s_full = bars + 9;
+  uint64_t* s_free = bars + 10;
+  uint64_t* p_full = bars + 11;
+  uint64_t* o_full = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q_tile = blockIdx.x;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int n_kv = (p.seq + kTile - 1) / kTile;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tm_qkv);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kKVStages; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_free, kSoftmaxThreads);
+    mbar_init(p_full, kSoftmaxThreads);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4) tmem_alloc<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ---------------- TMA + MMA issue (single thread) ----------------
+      constexpr uint32_t idesc_s = make_idesc_bf16(kTile, kTile, false, false);  // Q.K^T
+      constexpr uint32_t idesc_o = make_idesc_bf16(kTile, kD, false, true);      // P.V (V MN-major)
+      const int qc = p.q_off + head * kD, kc = p.k_off + head * kD, vc = p.v_off + head * kD;
+
+      mbar_expect_tx(q_full, kTileBytes);
+      tma_load_3d(sQ, &tm_qkv, q_full, qc, q_tile * kTile, b);
+      // prologue: first kKVStages K/V tiles
+      for (int j = 0; j < kKVStages && j < n_kv; ++j) {
+        mbar_expect_tx(&k_full[j], kTileBytes);
+        tma_load_3d(sK + j * kTileBytes, &tm_qkv, &k_full[j], kc, j * kTile, b);
+        mbar_expect_tx(&v_full[j], kTileBytes);
+        tma_load_3d(sV + j * kTileBytes, &tm_qkv, &v_full[j], vc, j * kTile, b);
+      }
+
+      const uint64_t dq = make_sdesc_sw128(smem_u32(sQ), 16, 1024);
+      auto issue_s = [&](int j) {
+        const int s = j % kKVStages;
+        mbar_wait(&k_full[s], (j / kKVStages) & 1);
+        tc_fence_after();
+        const uint64_t dk = make_sdesc_sw128(smem_u32(sK + s * kTileBytes), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k)
+          umma_ss(tmem + kColS, dq + uint64_t(2 * k), dk + uint64_t(2 * k), idesc_s, k != 0);
+        umma_commit(s_full);
+        umma_commit(&k_empty[s]);
+      };
+
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j % kKVStages;
+        if (j + 1 < n_kv) {
+          mbar_wait(s_free, j & 1);  // S_j is in registers: S columns reusable
+          issue_s(j + 1);
+          // S_j retired before s_full(j) fired, so K stage s is free: refill with K_{j+2}
+          if (j + kKVStages < n_kv) {
+            mbar_wait(&k_empty[s], (j / kKVStages) & 1);
+            mbar_expect_tx(&k_full[s], kTileBytes);
+            tma_load_3d(sK + s * kTileBytes, &tm_qkv, &k_full[s], kc, (j + kKVStages) * kTile, b);
+          }
+        }
+        mbar_wait(&v_full[s], (j / kKVStages) & 1);
+        mbar_wait(p_full, j & 1);  // P_j stored (and O rescaled if needed)
+        tc_fence_after();
+        // the softmax warps saw o_full(j-1) before storing P_j, so P.V_{j-1} retired and
+        // its V stage is free: refill it with V_{j+1} (V_0, V_1 came from the prologue)
+        if (j >= 1 && j + 1 < n_kv) {
+          const int sp = (j - 1) % kKVStages;
+          mbar_wait(&v_empty[sp], ((j - 1) / kKVStages) & 1);
+          mbar_expect_tx(&v_full[sp], kTileBytes);
+          tma_load_3d(sV + sp * kTileBytes, &tm_qkv, &v_full[sp], vc, (j + 1) * kTile, b);
+        }
+        {
+          // V tile [128 keys x 64 d], d contiguous: MN-major B operand.  One MMA
+          // consumes 16 keys = 16 rows of 128 B = 2 swizzle atoms (SBO 1024).
+          const uint32_t sv = smem_u32(sV + s * kTileBytes);
+#pragma unroll
+          for (int k = 0; k < kTile / 16; ++k) {
+            const uint64_t dv = make_sdesc_sw128(sv + k * 16 * 128, 16, 1024);
+            umma_ts(tmem + kColO, tmem + kColP + 8 * k, dv, idesc_o, (j | k) != 0);
+          }
+        }
+        umma_commit(o_full);
+        umma_commit(&v_empty[s]);
+      }
+    }
+  } else {
+    // ---------------- softmax warps: one query row per thread ----------------
+    const int row = warp * 32 + lane;  // row within the tile == TMEM lane
+    const uint32_t t_lane = tmem + (uint32_t(warp * 32) << 16);
+    float m_used = -INFINITY;  // in log2 units (already scaled)
+    float l = 0.0f;
+
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      uint32_t sraw[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_lane + kColS + c * 32, sraw[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_free);
+
+      const int valid = p.seq - j * kTile;  // keys valid in this tile (>= 1)
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float v = __uint_as_float(sraw[c][i]);
+          if (c * 32 + i >= valid) v = -INFINITY;
+          sraw[c][i] = __float_as_uint(v);
+          mx = fmaxf(mx, v);
+        }
+      const float m_new = fmaxf(m_used, mx * p.scale_log2);
+      // lazy max: keep the stale max while it is within 2^8 of the true one
+      const bool bump = (m_new - m_used) > 8.0f;
+      float alpha = 1.0f;
+      if (bump) {
+        alpha = exp2f(m_used - m_new);  // 0 on the first tile (m_used = -inf)
+        m_used = m_new;
+      }
+      float sum = 0.0f;
+      uint32_t pk[2][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float e0 = exp2f(fmaf(__uint_as_float(sraw[c][i]), p.scale_log2, -m_used));
+          const float e1 = exp2f(fmaf(__uint_as_float(sraw[c][i + 1]), p.scale_log2, -m_used));
+          sum += e0 + e1;
+          pk[c >> 1][((c & 1) * 32 + i) >> 1] = pack_bf16x2(e0, e1);
+        }
+      l = l * alpha + sum;
+
+      if (j > 0) {
+        mbar_wait(o_full, (j - 1) & 1);  // P.V of the previous tile retired
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, bump)) {
+          // rescale the running O row (rare after the first tiles)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32(t_lane + kColO + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32(t_lane + kColO + c * 32, o);
+          }
+        }
+      }
+      tmem_st_32x32(t_lane + kColP, pk[0]);
+      tmem_st_32x32(t_lane + kColP + 32, pk[1]);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+
+    // ---- epilogue: O / l -> ctx ----
+    mbar_wait(o_full, (n_kv - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    const int q_row = q_tile * kTile + row;
+    __nv_bfloat16* dst = p.ctx + (int64_t(b) * p.seq + q_row) * p.ldo + head * kD;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32(t_lane + kColO + c * 32, o);
+      tmem_ld_wait();
+      if (q_row < p.seq) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+          v.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+          v.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+          v.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(dst + c * 32 + i) = v;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem);
+  }
+}
+
+}  // namespace
+}  // namespace dod
+
+extern "C" int32_t dod_fmha_fwd(const dod_fmha_args* a, dod_stream_t stream_) {
+  using namespace dod;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DOD_REQUIRE(a && a->qkv && a->ctx, "dod_fmha_fwd: null pointer");
+  DOD_REQUIRE(a->batch > 0 && a->seq > 0 && a->heads > 0, "dod_fmha_fwd: empty problem");
+  DOD_REQUIRE(a->batch <= 65535 && a->heads <= 65535, "dod_fmha_fwd: batch/heads exceed grid limits");
+  DOD_REQUIRE(a->ld % 8 == 0 && a->ldo % 8 == 0, "dod_fmha_fwd: ld/ldo must be multiples of 8");
+  DOD_REQUIRE((uintptr_t(a->qkv) & 15) == 0 && (uintptr_t(a->ctx) & 15) == 0,
+              "dod_fmha_fwd: qkv/ctx must be 16-byte aligned");
+  DOD_REQUIRE(a->q_off % 8 == 0 && a->k_off % 8 == 0 && a->v_off % 8 == 0,
+              "dod_fmha_fwd: q/k/v column offsets must be multiples of 8");
+  DOD_REQUIRE(a->q_off + a->heads * kD <= a->ld && a->k_off + a->heads * kD <= a->ld &&
+                  a->v_off + a->heads * kD <= a->ld && a->heads * kD <= a->ldo,
+              "dod_fmha_fwd: head slices exceed the row");
+  static bool attr_set = false;
+  if (!attr_set) {
+    DOD_CUDA_OK(cudaFuncSetAttribute(fmha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kSmemBytes));
+    attr_set = true;
+  }
+  CUtensorMap tm;
+  if (int rc = make_tmap_3d(&tm, a->qkv, 2, a->batch, a->seq, a->ld, a->seq * a->ld, a->ld, kTile, kD))
+    return rc;
+  FmhaParams p;
+  p.seq = int(a->seq);
+  p.heads = int(a->heads);
+  p.q_off = int(a->q_off);
+  p.k_off = int(a->k_off);
+  p.v_off = int(a->v_off);
+  p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.ctx = reinterpret_cast<__nv_bfloat16*>(a->ctx);
+  p.ldo = a->ldo;
+  dim3 grid((a->seq + kTile - 1) / kTile, a->heads, a->batch);
+  fmha_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tm, p);
+  int rc = check_cuda(cudaGetLastError(), "fmha_kernel launch");
+  if (rc == 0) count_launch();
+  return rc;
+}

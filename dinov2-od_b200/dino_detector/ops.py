@@ -1,0 +1,212 @@
+"""Tensor-level wrappers over the libdod C ABI.
+
+PyTorch is used for device memory and streams only: every function here
+validates its arguments, allocates the output with torch.empty on the caller's
+device and launches the hand-written sm_100a kernel on torch's current stream.
+Nothing in this file computes with torch ops and nothing falls back to them.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _dod
+from ._dod import (ACT_GELU_ERF, ACT_NONE, ACT_RELU, ACT_SWIGLU, DOD_BF16, DOD_F32, DodError)
+
+_DT = {torch.bfloat16: DOD_BF16, torch.float32: DOD_F32}
+
+
+def _stream(t: torch.Tensor) -> int:
+    if not t.is_cuda:
+        raise DodError("libdod ops need CUDA tensors (no CPU fallback exists)")
+    _dod.check_device(t.device.index if t.device.index is not None else torch.cuda.current_device())
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _rowmajor(t: torch.Tensor, name: str):
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise DodError(f"{name}: expected a 2-D tensor with unit inner stride, got {tuple(t.shape)} "
+                       f"strides {t.stride()}")
+    return t.stride(0)
+
+
+def gemm(a, w, bias=None, *, act=ACT_NONE, scale=None, residual=None, out=None,
+         out_dtype=torch.bfloat16, a2=None, w2=None, patch_rows=0, out_rows=None):
+    """out = residual + scale * act(a @ w.T (+ a2 @ w2.T) + bias); a, w (a2, w2) bf16."""
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    lda, ldw = _rowmajor(a, "a"), _rowmajor(w, "w")
+    m, k = a.shape
+    n = w.shape[0]
+    assert w.shape[1] == k, (a.shape, w.shape)
+    n_out = n // 2 if act == ACT_SWIGLU else n
+    if out is None:
+        out = torch.empty((out_rows if out_rows is not None else m, n_out), dtype=out_dtype,
+                          device=a.device)
+    ldo = _rowmajor(out, "out")
+    kw = dict(a=a, w=w, m=m, n=n, k=k, lda=lda, ldw=ldw, bias=bias, act=act, scale=scale,
+              residual=residual, ldr=_rowmajor(residual, "residual") if residual is not None else 0,
+              out=out, ldo=ldo, out_dtype=_DT[out.dtype], patch_rows=patch_rows)
+    if a2 is not None:
+        assert a2.dtype == torch.bfloat16 and w2.dtype == torch.bfloat16
+        assert a2.shape[0] == m and w2.shape[0] == n and a2.shape[1] == w2.shape[1]
+        kw.update(a2=a2, w2=w2, k2=a2.shape[1], lda2=_rowmajor(a2, "a2"), ldw2=_rowmajor(w2, "w2"))
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() >= n
+    if scale is not None:
+        assert scale.dtype == torch.float32 and scale.numel() >= n
+    if residual is not None:
+        assert residual.dtype == torch.float32
+    _dod.call("dod_gemm_bf16", _stream(a), **kw)
+    return out
+
+
+def layernorm(x, gamma, beta, eps, *, out_dtype=torch.bfloat16, also_other=False, out=None):
+    """LayerNorm over the last dim of a 2-D tensor (f32 or bf16 in).  Returns y, or
+    (y, y_other_dtype) when also_other."""
+    ldx = _rowmajor(x, "x")
+    rows, d = x.shape
+    y = out if out is not None else torch.empty((rows, d), dtype=out_dtype, device=x.device)
+    y2 = None
+    if also_other:
+        other = torch.float32 if y.dtype == torch.bfloat16 else torch.bfloat16
+        y2 = torch.empty((rows, d), dtype=other, device=x.device)
+    _dod.call("dod_layernorm", _stream(x), x=x, x_dtype=_DT[x.dtype], gamma=gamma, beta=beta, y=y,
+              y_dtype=_DT[y.dtype], y2=y2, rows=rows, d=d, ldx=ldx, ldy=_rowmajor(y, "y"), eps=eps)
+    return (y, y2) if also_other else y
+
+
+def patchify14(pixels, kpad, *, cls=None, pos=None, tokens=None):
+    """im2col of 14x14 patches -> bf16 [B*P, kpad]; optionally writes the CLS rows of tokens."""
+    assert pixels.dtype == torch.float32 and pixels.is_contiguous() and pixels.dim() == 4
+    b, c, h, w = pixels.shape
+    if c != 3:
+        # same error as HF Dinov2PatchEmbeddings.forward (modeling_dinov2.py:143-147)
+        raise ValueError(
+            "Make sure that the channel dimension of the pixel values match with the one set in the "
+            f"configuration. Expected 3 but got {c}.")
+    p = (h // 14) * (w // 14)
+    patches = torch.empty((b * p, kpad), dtype=torch.bfloat16, device=pixels.device)
+    _dod.call("dod_patchify14", _stream(pixels), pixels=pixels, patches=patches, batch=b, height=h,
+              width=w, kpad=kpad, cls=cls, pos=pos, tokens=tokens,
+              d=tokens.shape[-1] if tokens is not None else 0)
+    return patches
+
+
+def pos_resize_bicubic(pos, g0, gh, gw):
+    """pos: f32 [1 + g0*g0, D] -> f32 [1 + gh*gw, D]."""
+    assert pos.dtype == torch.float32 and pos.is_contiguous()
+    d = pos.shape[1]
+    out = torch.empty((1 + gh * gw, d), dtype=torch.float32, device=pos.device)
+    _dod.call("dod_pos_resize_bicubic", _stream(pos), src=pos, dst=out, g0=g0, gh=gh, gw=gw, d=d)
+    return out
+
+
+def fmha(qkv, batch, seq, heads, *, q_off, k_off, v_off, scale, out=None):
+    """Self-attention over a fused projection buffer qkv [B*S, ld] (bf16), head dim 64."""
+    assert qkv.dtype == torch.bfloat16
+    ld = _rowmajor(qkv, "qkv")
+    assert qkv.shape[0] == batch * seq
+    if out is None:
+        out = torch.empty((batch * seq, heads * 64), dtype=torch.bfloat16, device=qkv.device)
+    _dod.call("dod_fmha_fwd", _stream(qkv), qkv=qkv, ctx=out, batch=batch, seq=seq, heads=heads,
+              ld=ld, ldo=_rowmajor(out, "out"), q_off=q_off, k_off=k_off, v_off=v_off, scale=scale)
+    return out
+
+
+def mha_small(q, k, v, batch, lq, lk, heads, head_dim, scale, out=None):
+    """Generic-head-dim attention with fp32 math; q/k/v are 2-D row views (bf16 or f32)."""
+    assert q.dtype == k.dtype == v.dtype
+    if out is None:
+        out = torch.empty((batch * lq, heads * head_dim), dtype=q.dtype, device=q.device)
+    _dod.call("dod_mha_small", _stream(q), q=q, k=k, v=v, out=out, batch=batch, lq=lq, lk=lk,
+              heads=heads, head_dim=head_dim, ldq=_rowmajor(q, "q"), ldk=_rowmajor(k, "k"),
+              ldv=_rowmajor(v, "v"), ldo=_rowmajor(out, "out"), scale=scale, dtype=_DT[q.dtype])
+    return out
+
+
+def deform_sample(value, ref, offs, logits, batch, queries, heads, points, head_dim, grid_h, grid_w,
+                  *, ref_is_logit=True, out_dtype=torch.bfloat16):
+    out = torch.empty((batch * queries, heads * head_dim), dtype=out_dtype, device=value.device)
+    _dod.call("dod_deform_sample", _stream(value), value=value, ref=ref, offs=offs, logits=logits,
+              out=out, batch=batch, queries=queries, heads=heads, points=points, head_dim=head_dim,
+              grid_h=grid_h, grid_w=grid_w, ldv=_rowmajor(value, "value"), ldref=_rowmajor(ref, "ref"),
+              ldoffs=_rowmajor(offs, "offs"), ldlog=_rowmajor(logits, "logits"),
+              ldo=_rowmajor(out, "out"), value_dtype=_DT[value.dtype], out_dtype=_DT[out.dtype],
+              ref_is_logit=int(ref_is_logit))
+    return out
+
+
+def rowcopy(x, n, *, sigmoid=False):
+    """out[r, :n] = act(x[r, :n]) as a contiguous f32 tensor."""
+    assert x.dtype == torch.float32
+    rows = x.shape[0]
+    out = torch.empty((rows, n), dtype=torch.float32, device=x.device)
+    _dod.call("dod_rowcopy", _stream(x), **{"in": x, "out": out, "rows": rows, "n": n,
+                                          "ld_in": _rowmajor(x, "x"), "ld_out": n,
+                                          "act": int(sigmoid)})
+    return out
+
+
+def broadcast_rows(src, batch, *, want_f32=True, want_bf16=True):
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    rows, d = src.shape
+    of = torch.empty((batch * rows, d), dtype=torch.float32, device=src.device) if want_f32 else None
+    ob = torch.empty((batch * rows, d), dtype=torch.bfloat16, device=src.device) if want_bf16 else None
+    _dod.call("dod_broadcast_rows", _stream(src), src=src, out=of, out_bf16=ob, batch=batch,
+              rows=rows, d=d)
+    return of, ob
+
+
+def cast_pad_bf16(src, dst_cols=None, *, scale=1.0, dst_rows=None):
+    """f32 [rows, cols] -> bf16 [dst_rows >= rows, dst_cols >= cols], zero padded."""
+    assert src.dtype == torch.float32
+    rows, cols = src.shape
+    dst_cols = dst_cols or cols
+    dst_rows = dst_rows or rows
+    if dst_rows > rows:
+        dst = torch.zeros((dst_rows, dst_cols), dtype=torch.bfloat16, device=src.device)
+    else:
+        dst = torch.empty((dst_rows, dst_cols), dtype=torch.bfloat16, device=src.device)
+    _dod.call("dod_cast_pad_bf16", _stream(src), src=src, dst=dst, rows=rows, cols=cols,
+              ld_src=_rowmajor(src, "src"), ld_dst=dst_cols, dst_cols=dst_cols, scale=scale)
+    return dst
+
+
+def split3_bf16(src, kseg, *, w_side, dst_rows=None):
+    """fp32 mode operand: f32 [rows, cols] -> bf16 [rows, 6*kseg] (see dod.h)."""
+    assert src.dtype == torch.float32
+    rows, cols = src.shape
+    dst_rows = dst_rows or rows
+    alloc = torch.zeros if dst_rows > rows else torch.empty
+    dst = alloc((dst_rows, 6 * kseg), dtype=torch.bfloat16, device=src.device)
+    _dod.call("dod_split3_bf16", _stream(src), src=src, dst=dst, rows=rows, cols=cols,
+              ld_src=_rowmajor(src, "src"), ld_dst=6 * kseg, kseg=kseg, w_side=int(w_side))
+    return dst
+
+
+def match_cost(logits, boxes, tgt_labels, tgt_boxes, tgt_offsets, max_t, *, w_class, w_bbox, w_giou,
+               alpha, gamma, use_image0_rows):
+    b, q, c = logits.shape
+    assert logits.dtype == torch.float32 and logits.is_contiguous()
+    assert boxes.dtype == torch.float32 and boxes.is_contiguous()
+    cost = torch.empty((b, q, max(max_t, 1)), dtype=torch.float32, device=logits.device)
+    if max_t > 0:
+        assert tgt_labels.dtype == torch.int64 and tgt_boxes.dtype == torch.float32
+        assert tgt_offsets.dtype == torch.int32
+        _dod.call("dod_match_cost", _stream(logits), logits=logits, boxes=boxes,
+                  tgt_labels=tgt_labels, tgt_boxes=tgt_boxes, tgt_offsets=tgt_offsets, cost=cost,
+                  batch=b, queries=q, classes=c, max_t=max_t, w_class=w_class, w_bbox=w_bbox,
+                  w_giou=w_giou, alpha=alpha, gamma=gamma, use_image0_rows=int(use_image0_rows))
+    return cost
+
+
+def lsap(cost, tgt_offsets, max_t):
+    """-> (out_q [B, K], out_t [B, K], status [B]) int32 on the device, K = min(Q, max_t)."""
+    b, q, ld = cost.shape
+    assert cost.dtype == torch.float32 and cost.is_contiguous() and ld >= max_t
+    k = max(min(q, max_t), 1)
+    out_q = torch.empty((b, k), dtype=torch.int32, device=cost.device)
+    out_t = torch.empty((b, k), dtype=torch.int32, device=cost.device)
+    status = torch.empty((b,), dtype=torch.int32, device=cost.device)
+    _dod.call("dod_lsap_jv", _stream(cost), cost=cost, tgt_offsets=tgt_offsets, out_q=out_q,
+              out_t=out_t, status=status, batch=b, queries=q, max_t=ld if max_t > 0 else 0, max_k=k)
+    return out_q, out_t, status

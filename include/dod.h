@@ -1,0 +1,260 @@
+/* libdod — C ABI of the B200-native (sm_100a) detector hot path.
+ *
+ * Drop-in boundary for mudit1729/dinov2-od: the reference has no FFI, its
+ * boundary is the Python module API `dino_detector.models` / `.matching`
+ * (reference dino_detector/models/detector.py:9-69, matching.py:9-122).  The
+ * Python host package in dinov2-od_b200/dino_detector mirrors that API and calls
+ * the entry points below through ctypes with raw device pointers.  Each entry
+ * point cites the reference (or third-party) code it replaces.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only, no torch / C++ types.
+ *   - every op is  int32_t dod_<op>(const dod_<op>_args*, dod_stream_t)  and
+ *     returns 0 on success or a negative dod_status; dod_last_error() gives a
+ *     thread-local message.
+ *   - ops never allocate, never synchronise and never touch the host copy of
+ *     the data: the caller owns all device memory and keeps it alive until the
+ *     stream has passed the op (PyTorch caching allocator + same stream).
+ *   - "bf16" buffers are raw 16-bit bfloat16, "f32" raw IEEE binary32.
+ *   - leading dimensions (ld*) are in ELEMENTS.
+ */
+#ifndef DOD_H_
+#define DOD_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* dod_stream_t; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define DOD_API __attribute__((visibility("default")))
+#else
+#define DOD_API
+#endif
+
+typedef enum {
+  DOD_OK = 0,
+  DOD_ERR_INVALID = -1,     /* bad argument / unsupported shape            */
+  DOD_ERR_CUDA = -2,        /* CUDA runtime / driver error                 */
+  DOD_ERR_DEVICE = -3,      /* not an sm_100 device                        */
+  DOD_ERR_UNSUPPORTED = -4  /* valid but not implemented                   */
+} dod_status;
+
+/* ---- library ---------------------------------------------------------- */
+DOD_API int32_t dod_version(void);              /* major*10000 + minor*100 + patch */
+DOD_API const char* dod_last_error(void);       /* thread-local, never NULL        */
+DOD_API int32_t dod_device_check(int32_t dev);  /* DOD_OK iff device is sm_100     */
+/* number of libdod kernels launched by this process since load / reset     */
+DOD_API int64_t dod_launch_count(void);
+DOD_API void dod_launch_count_reset(void);
+
+/* ---- dense contraction (tcgen05 / TMEM / TMA) ---------------------------
+ * out = residual + scale[n] * act( A[M,K] . W[N,K]^T  (+ A2[M,K2] . W2[N,K2]^T)  + bias[n] )
+ *
+ * Replaces every nn.Linear on the path: HF Dinov2 q/k/v, output.dense, fc1/fc2,
+ * weights_in/out (transformers modeling_dinov2.py:199-201,246-251,317-345),
+ * LoraLinear (reference utils.py:68-70: the rank-r update enters as the second
+ * K segment A2 = x.A^T (padded to a multiple of 64 columns), W2 = alpha*B),
+ * the patch-embedding conv-as-GEMM (modeling_dinov2.py:139,148), the backbone
+ * projection (dinov2_backbone.py:64-65) and the decoder projections.
+ */
+typedef enum { DOD_ACT_NONE = 0, DOD_ACT_GELU_ERF = 1, DOD_ACT_RELU = 2, DOD_ACT_SWIGLU = 3 } dod_act;
+typedef enum { DOD_BF16 = 0, DOD_F32 = 1 } dod_dtype;
+
+typedef struct {
+  const void* a;   /* bf16 [M, K], row stride lda (lda % 8 == 0, 16-B aligned) */
+  const void* w;   /* bf16 [N, K], row stride ldw (nn.Linear layout)           */
+  int64_t m, n, k, lda, ldw;
+  const void* a2;  /* optional second K segment (NULL: none)                  */
+  const void* w2;
+  int64_t k2, lda2, ldw2;
+  const float* bias;     /* f32 [N] or NULL                                   */
+  int32_t act;           /* dod_act.  SWIGLU: W rows interleaved in blocks of
+                            128 (gate) + 128 (linear); out has N/2 columns     */
+  const float* scale;    /* f32 [N] or NULL (LayerScale lambda)               */
+  const void* residual;  /* f32 [*, ldr] or NULL                              */
+  int64_t ldr;
+  void* out;             /* [M(.), N] bf16 or f32, row stride ldo             */
+  int64_t ldo;
+  int32_t out_dtype;     /* dod_dtype                                         */
+  /* patch-embedding row map: 0 = identity.  P > 0: GEMM row m is patch
+   * (m / P, m % P); it is stored at out row  m + m/P + 1  (token row, CLS
+   * skipped) and the residual row is  1 + m % P  (position embedding).       */
+  int32_t patch_rows;
+} dod_gemm_args;
+DOD_API int32_t dod_gemm_bf16(const dod_gemm_args* a, dod_stream_t stream);
+
+/* ---- LayerNorm (HBM-bound) ----------------------------------------------
+ * y = (x - mean) * rsqrt(var + eps) * gamma + beta, fp32 statistics.
+ * Replaces nn.LayerNorm at modeling_dinov2.py:354,359,449 (eps 1e-6) and the
+ * decoder's post-norms (deformable_attention.py:197-209, eps 1e-5).          */
+typedef struct {
+  const void* x;      /* [rows, d] f32 or bf16, row stride ldx                */
+  int32_t x_dtype;
+  const float* gamma; /* f32 [d]                                              */
+  const float* beta;  /* f32 [d]                                              */
+  void* y;            /* [rows, d] bf16 or f32, row stride ldy                */
+  int32_t y_dtype;
+  void* y2;           /* optional second copy of y in the other dtype or NULL */
+  int64_t rows, d, ldx, ldy;
+  float eps;
+} dod_layernorm_args;
+DOD_API int32_t dod_layernorm(const dod_layernorm_args* a, dod_stream_t stream);
+
+/* ---- patch embedding front end -------------------------------------------
+ * im2col of non-overlapping 14x14 patches + cast (modeling_dinov2.py:148:
+ * Conv2d(3, D, 14, 14) == GEMM over k = c*196 + i*14 + j).  Also writes the
+ * CLS rows  x[b*N + 0, :] = cls + pos[0]  (modeling_dinov2.py:108-112).       */
+typedef struct {
+  const float* pixels;  /* f32 [B, 3, H, W]                                   */
+  void* patches;        /* bf16 [B*P, kpad]  (kpad >= 588, kpad % 8 == 0)      */
+  int64_t batch, height, width, kpad;
+  const float* cls;     /* f32 [D]                                            */
+  const float* pos;     /* f32 [N, D] (already resized to this H, W)          */
+  float* tokens;        /* f32 [B*N, D] residual stream; only CLS rows written */
+  int64_t d;
+} dod_patchify_args;
+DOD_API int32_t dod_patchify14(const dod_patchify_args* a, dod_stream_t stream);
+
+/* bicubic (A=-0.75, align_corners=False) resize of the [G0,G0,D] position grid
+ * to [GH,GW,D] in fp32 — F.interpolate call at modeling_dinov2.py:84-89.      */
+typedef struct {
+  const float* src; /* f32 [1 + g0*g0, D] (row 0 = CLS position)              */
+  float* dst;       /* f32 [1 + gh*gw, D]                                     */
+  int64_t g0, gh, gw, d;
+} dod_pos_resize_args;
+DOD_API int32_t dod_pos_resize_bicubic(const dod_pos_resize_args* a, dod_stream_t stream);
+
+/* ---- fused multi-head self-attention (tcgen05, flash-style) --------------
+ * ctx = softmax(Q K^T * scale) V per (batch, head); non-causal, no mask.
+ * Replaces SDPA at modeling_dinov2.py:215-229.  q/k/v are column slices of one
+ * fused projection buffer qkv[B*S, ld]: head h of q at columns q_off + h*64.  */
+typedef struct {
+  const void* qkv; /* bf16 [B*S, ld]                                          */
+  void* ctx;       /* bf16 [B*S, ldo], head h at columns h*64                  */
+  int64_t batch, seq, heads, ld, ldo;
+  int64_t q_off, k_off, v_off; /* column offsets (elements)                    */
+  float scale;     /* 1/sqrt(64)                                              */
+} dod_fmha_args;
+DOD_API int32_t dod_fmha_fwd(const dod_fmha_args* a, dod_stream_t stream);
+
+/* ---- decoder attention with few queries (generic head dim) ---------------
+ * nn.MultiheadAttention core (torch) used at deformable_attention.py:232-233
+ * and inside nn.TransformerDecoderLayer (detr_decoder.py:29-35):
+ * out[b, q, h*dh:(h+1)*dh] = softmax(Qh Kh^T / sqrt(dh)) Vh.
+ * q: [B*Lq, ldq], k/v: [B*Lk, ldk/ldv], out [B*Lq, ldo]; fp32 math.  Also used
+ * for the backbone attention in fp32 mode (any sequence that fits the
+ * shared-memory score tile: Lk <= ~3000).                                     */
+typedef struct {
+  const void* q; const void* k; const void* v; void* out;
+  int64_t batch, lq, lk, heads, head_dim;
+  int64_t ldq, ldk, ldv, ldo;
+  float scale;
+  int32_t dtype;   /* dod_dtype of q, k, v and out (f32 = fp32 mode)          */
+} dod_mha_small_args;
+DOD_API int32_t dod_mha_small(const dod_mha_small_args* a, dod_stream_t stream);
+
+/* ---- "deformable" sampling (reference deformable_attention.py:100-178) ---
+ * For each (b, q, head, point): loc = clamp(ref + off, 0, 1); bilinear blend of
+ * 4 value rows (memory index y*w + x, CLS included), weighted by softmax over
+ * points of attention logits.                                                 */
+typedef struct {
+  const void* value;   /* [B*hw, ldv]  value_proj(memory), bf16 or f32         */
+  const float* ref;    /* f32  [B*Q, ldref]  reference point (x, y) in cols 0,1 */
+  const float* offs;   /* f32  [B*Q, ldoffs] sampling_offsets(query): H*P*2    */
+  const float* logits; /* f32  [B*Q, ldlog]  attention_weights(query): H*P     */
+  void* out;           /* [B*Q, ldo] bf16 or f32                               */
+  int64_t batch, queries, heads, points, head_dim, grid_h, grid_w;
+  int64_t ldv, ldref, ldoffs, ldlog, ldo;
+  int32_t value_dtype, out_dtype; /* dod_dtype                                 */
+  int32_t ref_is_logit; /* 1: apply sigmoid to ref (reference_points_proj output,
+                           deformable_attention.py:238) inside the kernel      */
+} dod_deform_sample_args;
+DOD_API int32_t dod_deform_sample(const dod_deform_sample_args* a, dod_stream_t stream);
+
+/* ---- small elementwise helpers of the decoder ---------------------------- */
+/* y = LayerNorm(x + r) (post-norm residual, deformable_attention.py:234-235)  */
+typedef struct {
+  const float* x; const void* r; int32_t r_dtype;
+  const float* gamma; const float* beta;
+  float* y; void* y_bf16; /* y_bf16 optional                                  */
+  int64_t rows, d; float eps;
+} dod_add_layernorm_args;
+DOD_API int32_t dod_add_layernorm(const dod_add_layernorm_args* a, dod_stream_t stream);
+
+/* out[r, :n] = act(in[r, :n]) with f32 -> f32: act 0 copy, 1 sigmoid          */
+typedef struct {
+  const float* in; float* out; int64_t rows, n, ld_in, ld_out; int32_t act;
+} dod_rowcopy_args;
+DOD_API int32_t dod_rowcopy(const dod_rowcopy_args* a, dod_stream_t stream);
+
+/* broadcast rows: out[b*rows + r, :] = src[r, :] (query_embed repeat,
+ * detr_decoder.py:59), f32 and bf16 copies                                    */
+typedef struct {
+  const float* src; float* out; void* out_bf16; int64_t batch, rows, d;
+} dod_broadcast_rows_args;
+DOD_API int32_t dod_broadcast_rows(const dod_broadcast_rows_args* a, dod_stream_t stream);
+
+/* f32 -> bf16 cast of a [rows, cols] matrix into a (possibly wider, zero
+ * padded) destination: dst[r, c] = c < cols ? scale*src[r, c] : 0             */
+typedef struct {
+  const float* src; void* dst; int64_t rows, cols, ld_src, ld_dst, dst_cols; float scale;
+} dod_cast_pad_args;
+DOD_API int32_t dod_cast_pad_bf16(const dod_cast_pad_args* a, dod_stream_t stream);
+
+/* fp32 mode: split an f32 matrix into three bf16 terms (x = hi + mid + lo) and
+ * lay the six K segments out so that ONE dod_gemm_bf16 call with fp32
+ * accumulation reproduces the fp32 product to ~2^-22 relative:
+ *   activation side (w_side 0): [hi | hi  | mid | hi | lo | mid]
+ *   weight side     (w_side 1): [hi | mid | hi  | lo | hi | mid]
+ * dst is [rows, 6*kseg] bf16 (kseg >= cols, kseg % 8 == 0, zero padded).      */
+typedef struct {
+  const float* src; void* dst; int64_t rows, cols, ld_src, ld_dst, kseg; int32_t w_side;
+} dod_split3_args;
+DOD_API int32_t dod_split3_bf16(const dod_split3_args* a, dod_stream_t stream);
+
+/* ---- Hungarian matcher ----------------------------------------------------
+ * Cost matrix (reference matching.py:63,80-98):
+ *   C[q, j] = (wc*(pos[q, lab_j] - neg[q, lab_j]) + wb*L1(box_q, box_j)) + wg*(-GIoU)
+ * for every image b over its own n_b targets; targets are packed (CSR offsets).
+ * pred_image_stride == 0 reproduces the reference quirk (matching.py:102) that
+ * the rows of image 0 are used for every image.                               */
+typedef struct {
+  const float* logits;   /* f32 [B, Q, C]                                     */
+  const float* boxes;    /* f32 [B, Q, 4] cxcywh                              */
+  const int64_t* tgt_labels; /* i64 [T]                                       */
+  const float* tgt_boxes;    /* f32 [T, 4]                                    */
+  const int32_t* tgt_offsets; /* i32 [B+1] CSR                                */
+  float* cost;           /* f32 [B, Q, max_t] (row stride max_t)              */
+  int64_t batch, queries, classes, max_t;
+  float w_class, w_bbox, w_giou, alpha, gamma;
+  int32_t use_image0_rows; /* 1 = reference_compat                            */
+} dod_match_cost_args;
+DOD_API int32_t dod_match_cost(const dod_match_cost_args* a, dod_stream_t stream);
+
+/* Rectangular linear sum assignment, bit-identical to
+ * scipy.optimize.linear_sum_assignment (scipy 1.18.1 _lsap, Crouse 2016
+ * shortest augmenting path in float64; call site matching.py:105) on the same
+ * fp32 cost.  One problem per image: rows = queries (Q), cols = n_b targets;
+ * like scipy the solver transposes when n_b < Q.  Output per image b:
+ * k_b = min(Q, n_b) pairs (out_q[b, i], out_t[b, i]) sorted by query index,
+ * exactly the (row_ind, col_ind) arrays scipy returns.
+ * status[b]: 0 ok, 1 = cost has NaN / -inf entries or is infeasible (scipy
+ * raises ValueError there).                                                    */
+typedef struct {
+  const float* cost;          /* f32 [B, Q, max_t]                            */
+  const int32_t* tgt_offsets; /* i32 [B+1]                                    */
+  int32_t* out_q;             /* i32 [B, max_k]                               */
+  int32_t* out_t;             /* i32 [B, max_k]                               */
+  int32_t* status;            /* i32 [B]                                      */
+  int64_t batch, queries, max_t, max_k;
+} dod_lsap_args;
+DOD_API int32_t dod_lsap_jv(const dod_lsap_args* a, dod_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DOD_H_ */

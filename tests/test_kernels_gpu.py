@@ -1,0 +1,336 @@
+"""Kernel-level parity: every libdod op against a plain PyTorch fp32 restatement
+of the same arithmetic on the same seeded inputs (B200 only)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from dino_detector import ops as _ops
+    return _ops
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-6)).item()
+
+
+def _gen(seed):
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    return g
+
+
+def _randn(shape, g, scale=1.0):
+    return (torch.randn(shape, generator=g) * scale).cuda()
+
+
+# --------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("m,n,k", [
+    (128, 64, 64), (128, 128, 128), (256, 256, 256), (300, 768, 768), (1000, 2304, 768),
+    (87, 96, 392), (2740, 3072, 768), (513, 56, 768), (4096, 768, 3072), (129, 8, 64),
+    (5000, 1024, 592),
+])
+def test_gemm_plain(ops, m, n, k):
+    g = _gen(m * 7 + n * 3 + k)
+    a = _randn((m, k), g).bfloat16()
+    w = _randn((n, k), g, 1 / math.sqrt(k)).bfloat16()
+    bias = _randn((n,), g)
+    out = ops.gemm(a, w, bias, out_dtype=torch.float32)
+    ref = a.float() @ w.float().t() + bias
+    assert _rel(out, ref) < 2e-5
+    out_b = ops.gemm(a, w, bias)
+    assert out_b.dtype == torch.bfloat16
+    assert _rel(out_b, ref) < 1e-2
+
+
+@pytest.mark.parametrize("act", ["gelu", "relu"])
+def test_gemm_act_scale_residual(ops, act):
+    m, n, k = 777, 384, 320
+    g = _gen(11)
+    a = _randn((m, k), g).bfloat16()
+    w = _randn((n, k), g, 1 / math.sqrt(k)).bfloat16()
+    bias, scale = _randn((n,), g), _randn((n,), g)
+    res = _randn((m, n), g)
+    code = ops.ACT_GELU_ERF if act == "gelu" else ops.ACT_RELU
+    out = ops.gemm(a, w, bias, act=code, scale=scale, residual=res, out_dtype=torch.float32)
+    z = a.float() @ w.float().t() + bias
+    z = torch.nn.functional.gelu(z) if act == "gelu" else torch.relu(z)
+    ref = res + scale * z
+    assert _rel(out, ref) < 2e-5
+
+
+def test_gemm_second_k_segment(ops):
+    """LoRA as a second K segment: x.W^T + (x.A^T).(alpha B)^T."""
+    m, n, k, r = 900, 768, 768, 8
+    g = _gen(5)
+    x = _randn((m, k), g).bfloat16()
+    w = _randn((n, k), g, 1 / math.sqrt(k)).bfloat16()
+    t = torch.zeros((m, 64), dtype=torch.bfloat16, device="cuda")
+    t[:, :r] = _randn((m, r), g).bfloat16()
+    bw = torch.zeros((n, 64), dtype=torch.bfloat16, device="cuda")
+    bw[:, :r] = _randn((n, r), g).bfloat16()
+    out = ops.gemm(x, w, None, a2=t, w2=bw, out_dtype=torch.float32)
+    ref = x.float() @ w.float().t() + t.float() @ bw.float().t()
+    assert _rel(out, ref) < 2e-5
+
+
+def test_gemm_swiglu(ops):
+    m, k, hidden = 500, 256, 512
+    g = _gen(6)
+    x = _randn((m, k), g).bfloat16()
+    w_in = _randn((2 * hidden, k), g, 1 / math.sqrt(k))
+    b_in = _randn((2 * hidden,), g)
+    # interleave gate / linear halves in blocks of 128 rows (see dod.h)
+    idx = []
+    for blk in range(hidden // 128):
+        idx += list(range(blk * 128, blk * 128 + 128))
+        idx += list(range(hidden + blk * 128, hidden + blk * 128 + 128))
+    idx = torch.tensor(idx, device="cuda")
+    out = ops.gemm(x, w_in[idx].bfloat16().contiguous(), b_in[idx].contiguous(), act=ops.ACT_SWIGLU)
+    z = x.float() @ w_in.bfloat16().float().t() + b_in
+    ref = torch.nn.functional.silu(z[:, :hidden]) * z[:, hidden:]
+    assert out.shape == (m, hidden)
+    assert _rel(out, ref) < 1e-2
+
+
+def test_gemm_patch_rows(ops):
+    """Patch-embedding row map: GEMM row m -> token row m + m/P + 1, residual row 1 + m%P."""
+    b, p, k, d = 3, 16, 592, 384
+    g = _gen(8)
+    a = _randn((b * p, k), g).bfloat16()
+    w = _randn((d, k), g, 1 / math.sqrt(k)).bfloat16()
+    bias = _randn((d,), g)
+    pos = _randn((p + 1, d), g)
+    tokens = torch.full((b * (p + 1), d), -7.0, device="cuda")
+    ops.gemm(a, w, bias, residual=pos, out=tokens, patch_rows=p)
+    ref = (a.float() @ w.float().t() + bias).view(b, p, d) + pos[1:]
+    got = tokens.view(b, p + 1, d)
+    assert _rel(got[:, 1:], ref) < 2e-5
+    assert (got[:, 0] == -7.0).all()
+
+
+def test_gemm_fp32_mode_split3(ops):
+    """3-term bf16 split on both operands reproduces the fp32 product."""
+    m, n, k = 515, 384, 384
+    g = _gen(9)
+    a, w = _randn((m, k), g), _randn((n, k), g, 1 / math.sqrt(k))
+    a6 = ops.split3_bf16(a, k, w_side=False)
+    w6 = ops.split3_bf16(w, k, w_side=True)
+    out = ops.gemm(a6, w6, None, out_dtype=torch.float32)
+    ref = (a.double() @ w.double().t()).float()
+    assert _rel(out, ref) < 2e-6
+
+
+# ----------------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("d", [256, 384, 768, 1024, 1536])
+@pytest.mark.parametrize("xdt", [torch.float32, torch.bfloat16])
+def test_layernorm(ops, d, xdt):
+    g = _gen(d)
+    x = (_randn((1001, d), g) * 3 + 1).to(xdt)
+    gamma, beta = _randn((d,), g), _randn((d,), g)
+    y32, y16 = ops.layernorm(x, gamma, beta, 1e-6, out_dtype=torch.float32, also_other=True)
+    ref = torch.nn.functional.layer_norm(x.float(), (d,), gamma, beta, 1e-6)
+    assert _rel(y32, ref) < 1e-5
+    assert _rel(y16, ref) < 1e-2
+
+
+# ------------------------------------------------------------------- patch embedding
+def test_patchify_and_pos_resize(ops):
+    g = _gen(3)
+    b, h, w, d = 2, 42, 56, 64
+    px = torch.rand((b, 3, h, w), generator=g).cuda()
+    cls, pos = _randn((d,), g), _randn((1 + 12, d), g)
+    tokens = torch.zeros((b * 13, d), device="cuda")
+    patches = ops.patchify14(px, 592, cls=cls, pos=pos, tokens=tokens)
+    ref = torch.nn.functional.unfold(px, 14, stride=14).transpose(1, 2).reshape(b * 12, 588)
+    assert torch.equal(patches[:, :588], ref.bfloat16())
+    assert (patches[:, 588:] == 0).all()
+    assert torch.allclose(tokens.view(b, 13, d)[:, 0], (cls + pos[0]).expand(b, d))
+    # bicubic resize of a 37x37 grid to 16x16 (HF interpolate_pos_encoding, 224px input)
+    pe = _randn((1 + 37 * 37, d), g)
+    out = ops.pos_resize_bicubic(pe, 37, 16, 16)
+    grid = pe[1:].view(1, 37, 37, d).permute(0, 3, 1, 2)
+    ref = torch.nn.functional.interpolate(grid, size=(16, 16), mode="bicubic", align_corners=False)
+    ref = ref.permute(0, 2, 3, 1).reshape(256, d)
+    assert torch.allclose(out[1:], ref, atol=2e-5, rtol=1e-5)
+    assert torch.equal(out[0], pe[0])
+
+
+# ----------------------------------------------------------------------- attention
+@pytest.mark.parametrize("b,s,h", [(1, 128, 1), (2, 257, 6), (1, 1370, 12), (3, 100, 2), (2, 384, 3)])
+def test_fmha(ops, b, s, h):
+    g = _gen(s + h)
+    d = h * 64
+    qkv = _randn((b * s, 3 * d), g).bfloat16()
+    out = ops.fmha(qkv, b, s, h, q_off=0, k_off=d, v_off=2 * d, scale=0.125)
+    q, k, v = (qkv.float().view(b, s, 3, h, 64).permute(2, 0, 3, 1, 4))
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v)
+    ref = ref.permute(0, 2, 1, 3).reshape(b * s, d)
+    assert _rel(out, ref) < 2e-2
+    assert (out.float() - ref).abs().max().item() < 2e-2
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("b,lq,lk,h,dh", [(2, 50, 50, 8, 96), (3, 100, 257, 4, 64), (1, 25, 1370, 8, 96),
+                                          (2, 17, 33, 4, 192)])
+def test_mha_small(ops, dt, b, lq, lk, h, dh):
+    g = _gen(lq + lk)
+    d = h * dh
+    q, k, v = (_randn((b * lq, d), g).to(dt), _randn((b * lk, d), g).to(dt), _randn((b * lk, d), g).to(dt))
+    out = ops.mha_small(q, k, v, b, lq, lk, h, dh, 1 / math.sqrt(dh))
+    qf = q.float().view(b, lq, h, dh).transpose(1, 2)
+    kf = k.float().view(b, lk, h, dh).transpose(1, 2)
+    vf = v.float().view(b, lk, h, dh).transpose(1, 2)
+    ref = torch.nn.functional.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(b * lq, d)
+    assert _rel(out, ref) < (1e-2 if dt == torch.bfloat16 else 1e-5)
+
+
+def _deform_ref(value, ref_pts, offs, logits, b, q, h, p, dh, gh, gw):
+    """Vectorised restatement of reference deformable_attention.py:100-178."""
+    offs = offs.view(b, q, h, p, 2)
+    wts = logits.view(b, q, h, p).softmax(-1)
+    loc = (ref_pts.view(b, q, 1, 1, 2) + offs).clamp(0, 1)
+    sx, sy = loc[..., 0] * (gw - 1), loc[..., 1] * (gh - 1)
+    x0, y0 = torch.floor(sx).long(), torch.floor(sy).long()
+    x1, y1 = (x0 + 1).clamp(0, gw - 1), (y0 + 1).clamp(0, gh - 1)
+    x0, y0 = x0.clamp(0, gw - 1), y0.clamp(0, gh - 1)
+    wx1, wy1 = sx - x0.float(), sy - y0.float()
+    wx0, wy0 = 1 - wx1, 1 - wy1
+    vh = value.float().view(b, gh * gw, h, dh)
+    bi = torch.arange(b, device=value.device).view(b, 1, 1, 1)
+    hi = torch.arange(h, device=value.device).view(1, 1, h, 1)
+    def gat(yy, xx):
+        return vh[bi, yy * gw + xx, hi]
+    samp = (gat(y0, x0) * (wx0 * wy0)[..., None] + gat(y1, x0) * (wx0 * wy1)[..., None]
+            + gat(y0, x1) * (wx1 * wy0)[..., None] + gat(y1, x1) * (wx1 * wy1)[..., None])
+    return (samp * wts[..., None]).sum(3).reshape(b * q, h * dh)
+
+
+@pytest.mark.parametrize("gh,gw", [(10, 137), (1, 257), (16, 16)])
+def test_deform_sample(ops, gh, gw):
+    g = _gen(gh)
+    b, q, h, p, dh = 2, 50, 8, 2, 96
+    value = _randn((b * gh * gw, h * dh), g)
+    raw = _randn((b * q, 56), g)  # [offsets 32 | logits 16 | ref logits 2 | pad]
+    out = ops.deform_sample(value, raw[:, 48:50], raw[:, :32], raw[:, 32:48], b, q, h, p, dh, gh, gw,
+                            ref_is_logit=True, out_dtype=torch.float32)
+    ref = _deform_ref(value, raw[:, 48:50].sigmoid(), raw[:, :32], raw[:, 32:48], b, q, h, p, dh, gh, gw)
+    assert torch.allclose(out, ref, atol=1e-5, rtol=1e-5)
+    out16 = ops.deform_sample(value.bfloat16(), raw[:, 48:50], raw[:, :32], raw[:, 32:48], b, q, h, p,
+                              dh, gh, gw)
+    assert _rel(out16, ref) < 2e-2
+
+
+def test_row_utils(ops):
+    g = _gen(1)
+    x = _randn((77, 96), g)
+    assert torch.equal(ops.rowcopy(x, 91), x[:, :91])
+    assert torch.allclose(ops.rowcopy(x, 4, sigmoid=True), x[:, :4].sigmoid(), atol=1e-6)
+    src = _randn((50, 64), g)
+    f, h = ops.broadcast_rows(src, 3)
+    assert torch.equal(f.view(3, 50, 64), src.expand(3, 50, 64))
+    assert torch.equal(h, f.bfloat16())
+    c = ops.cast_pad_bf16(x, 128, scale=2.0, dst_rows=80)
+    assert torch.equal(c[:77, :96], (2 * x).bfloat16()) and (c[:, 96:] == 0).all() and (c[77:] == 0).all()
+
+
+# ------------------------------------------------------------------------- matcher
+def _targets(bs, g, max_n=50, classes=91):
+    labels, boxes, offs = [], [], [0]
+    for _ in range(bs):
+        n = int(torch.randint(0, max_n + 1, (1,), generator=g))
+        labels.append(torch.randint(0, classes, (n,), generator=g))
+        cxcy = torch.rand((n, 2), generator=g) * 0.6 + 0.2
+        wh = torch.rand((n, 2), generator=g) * 0.3 + 0.02
+        boxes.append(torch.cat([cxcy, wh], 1))
+        offs.append(offs[-1] + n)
+    return labels, boxes, offs
+
+
+@pytest.mark.parametrize("image0", [True, False])
+def test_match_cost_and_lsap_vs_scipy(ops, image0):
+    from scipy.optimize import linear_sum_assignment
+    g = _gen(0)
+    bs, q, c = 64, 100, 91
+    logits = torch.randn((bs, q, c), generator=g).cuda()
+    pboxes = (torch.rand((bs, q, 4), generator=g) * 0.5 + 0.25).cuda()
+    labels, boxes, offs = _targets(bs, g)
+    max_t = max(len(l) for l in labels)
+    cost = ops.match_cost(logits, pboxes, torch.cat(labels).cuda(), torch.cat(boxes).cuda(),
+                          torch.tensor(offs, dtype=torch.int32).cuda(), max_t, w_class=1.0, w_bbox=5.0,
+                          w_giou=2.0, alpha=0.25, gamma=2.0, use_image0_rows=image0)
+    oq, ot, status = ops.lsap(cost, torch.tensor(offs, dtype=torch.int32).cuda(), max_t)
+    cost_h, oq, ot, status = cost.cpu(), oq.cpu(), ot.cpu(), status.cpu()
+    assert (status == 0).all()
+    for b in range(bs):
+        n = len(labels[b])
+        # (i) cost vs the reference formula (matching.py:80-98) in torch fp32 on the CPU
+        src = 0 if image0 else b
+        p = logits[src].cpu().sigmoid()
+        neg = 0.75 * (p ** 2.0) * (-(1 - p + 1e-8).log())
+        pos = 0.25 * ((1 - p) ** 2.0) * (-(p + 1e-8).log())
+        cc = pos[:, labels[b]] - neg[:, labels[b]]
+        pb = pboxes[src].cpu()
+        cb = torch.cdist(pb, boxes[b], p=1) if n else torch.zeros((q, 0))
+        def xyxy(x):
+            return torch.stack([x[:, 0] - 0.5 * x[:, 2], x[:, 1] - 0.5 * x[:, 3],
+                                x[:, 0] + 0.5 * x[:, 2], x[:, 1] + 0.5 * x[:, 3]], -1)
+        b1, b2 = xyxy(pb), xyxy(boxes[b])
+        a1 = (b1[:, 2] - b1[:, 0]) * (b1[:, 3] - b1[:, 1])
+        a2 = (b2[:, 2] - b2[:, 0]) * (b2[:, 3] - b2[:, 1])
+        wh = (torch.min(b1[:, None, 2:], b2[:, 2:]) - torch.max(b1[:, None, :2], b2[:, :2])).clamp(min=0)
+        inter = wh[..., 0] * wh[..., 1]
+        union = a1[:, None] + a2 - inter
+        whe = (torch.max(b1[:, None, 2:], b2[:, 2:]) - torch.min(b1[:, None, :2], b2[:, :2])).clamp(min=0)
+        ae = whe[..., 0] * whe[..., 1]
+        giou = inter / union - (ae - union) / ae
+        ref = 1.0 * cc + 5.0 * cb + 2.0 * (-giou)
+        assert torch.allclose(cost_h[b, :, :n], ref, atol=2e-5, rtol=1e-5)
+        # (ii) assignment bit-identical to scipy on OUR fp32 cost matrix
+        ri, ci = linear_sum_assignment(cost_h[b, :, :n].numpy())
+        k = min(q, n)
+        assert np.array_equal(oq[b, :k].numpy(), ri) and np.array_equal(ot[b, :k].numpy(), ci)
+
+
+def test_lsap_ties_and_shapes(ops):
+    """Adversarial assignment problems: constant / integer-tie / duplicate-column costs,
+    n = 0, n = Q and n > Q (no transpose)."""
+    from scipy.optimize import linear_sum_assignment
+    g = _gen(4)
+    q = 20
+    cases = []
+    for n in [0, 1, 5, 19, 20, 21, 37]:
+        cases.append(torch.zeros((q, n)))
+        cases.append(torch.randint(0, 3, (q, n), generator=g).float())
+        cases.append(torch.rand((q, n), generator=g))
+        if n >= 2:
+            dup = torch.rand((q, n), generator=g)
+            dup[:, 1] = dup[:, 0]
+            dup[3] = dup[2]
+            cases.append(dup)
+    max_t = max(c.shape[1] for c in cases)
+    bs = len(cases)
+    cost = torch.zeros((bs, q, max_t))
+    offs = [0]
+    for i, c in enumerate(cases):
+        cost[i, :, :c.shape[1]] = c
+        offs.append(offs[-1] + c.shape[1])
+    oq, ot, status = ops.lsap(cost.cuda(), torch.tensor(offs, dtype=torch.int32).cuda(), max_t)
+    oq, ot, status = oq.cpu().numpy(), ot.cpu().numpy(), status.cpu().numpy()
+    assert (status == 0).all()
+    for i, c in enumerate(cases):
+        ri, ci = linear_sum_assignment(c.numpy())
+        k = min(q, c.shape[1])
+        assert np.array_equal(oq[i, :k], ri), (i, c.shape)
+        assert np.array_equal(ot[i, :k], ci), (i, c.shape)
+    # NaN cost -> status 1 (scipy raises ValueError)
+    bad = torch.rand((1, q, 4))
+    bad[0, 3, 2] = float("nan")
+    _, _, st = ops.lsap(bad.cuda(), torch.tensor([0, 4], dtype=torch.int32).cuda(), 4)
+    assert st.cpu().item() == 1
