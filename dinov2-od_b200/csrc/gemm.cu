@@ -208,15 +208,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
               }
               r[j] = silu(gv) * uv;
             }
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldo + n_out;
+            if (p.out_f32) {
+              float* o = reinterpret_cast<float*>(p.out) + out_row * p.ldo + n_out;
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 v;
-              v.x = pack_bf16x2(r[j], r[j + 1]);
-              v.y = pack_bf16x2(r[j + 2], r[j + 3]);
-              v.z = pack_bf16x2(r[j + 4], r[j + 5]);
-              v.w = pack_bf16x2(r[j + 6], r[j + 7]);
-              *reinterpret_cast<uint4*>(o + j) = v;
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(o + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+            } else {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldo + n_out;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                uint4 v;
+                v.x = pack_bf16x2(r[j], r[j + 1]);
+                v.y = pack_bf16x2(r[j + 2], r[j + 3]);
+                v.z = pack_bf16x2(r[j + 4], r[j + 5]);
+                v.w = pack_bf16x2(r[j + 6], r[j + 7]);
+                *reinterpret_cast<uint4*>(o + j) = v;
+              }
             }
           }
         }
@@ -388,9 +395,8 @@ extern "C" int32_t dod_gemm_bf16(const dod_gemm_args* a, dod_stream_t stream_) {
   if (a->scale) DOD_REQUIRE((uintptr_t(a->scale) & 15) == 0, "dod_gemm_bf16: scale alignment");
   int rc;
   if (a->act == DOD_ACT_SWIGLU) {
-    DOD_REQUIRE(a->n % 256 == 0 && !a->scale && !a->residual && a->out_dtype == DOD_BF16 &&
-                    a->patch_rows == 0,
-                "dod_gemm_bf16: SWIGLU needs n %% 256 == 0, bf16 out, no scale/residual");
+    DOD_REQUIRE(a->n % 256 == 0 && !a->scale && !a->residual && a->patch_rows == 0,
+                "dod_gemm_bf16: SWIGLU needs n %% 256 == 0 and no scale/residual");
     rc = launch<256>(*a, stream);
   } else if (a->n > 128) {
     rc = launch<256>(*a, stream);

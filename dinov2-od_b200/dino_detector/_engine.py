@@ -1,0 +1,384 @@
+"""Host-side execution engine: weight packing and the kernel sequences of the detector.
+
+Nothing here does arithmetic on activations with torch ops: torch supplies device
+memory (torch.empty) and the current stream; every transformation of activations is
+a libdod kernel (include/dod.h).  Weight *packing* (concatenation, zero padding,
+row interleaving of frozen or small trainable tensors) uses torch indexing/copies
+once per weight version and is cached.
+
+Precision modes
+  bf16  operands bf16, fp32 accumulation in TMEM, fp32 residual stream, fp32 LayerNorm
+        statistics.  LoRA enters the base GEMM as a second K segment
+        (A2 = x.A^T padded to 64 columns, W2 = alpha.B), see dod_gemm_bf16.
+  fp32  every GEMM operand is split into three bf16 terms (dod_split3_bf16) and the six
+        significant partial products run as six K segments of ONE tcgen05 GEMM with
+        fp32 accumulation; attention uses the fp32 CUDA-core kernel (dod_mha_small).
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import torch
+
+from . import config, ops
+from .ops import ACT_GELU_ERF, ACT_NONE, ACT_RELU, ACT_SWIGLU
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+def resolve_precision(module_precision=None):
+    p = module_precision or os.environ.get("DOD_PRECISION") or config.precision
+    if p not in ("bf16", "fp32"):
+        raise ValueError(f"precision must be 'bf16' or 'fp32', got {p!r}")
+    return p
+
+
+# ---------------------------------------------------------------------------
+# packed linear layers
+# ---------------------------------------------------------------------------
+class PackedLinear:
+    """W [N, K] (+ bias, + optional LoRA pair) packed for dod_gemm_bf16 in one precision mode.
+
+    n      logical output features;  n_pad = n rounded up to 8 (zero rows)
+    w      bf16 [n_pad, K] (bf16 mode)  |  bf16 [n_pad, 6*kseg] (fp32 mode)
+    bias   f32 [n_pad] or None
+    lora   None or (PackedLinear for x -> t, packed alpha*B as second K segment, k2)
+    """
+
+    def __init__(self, weight, bias, mode, *, lora=None, swiglu_interleave=False):
+        # weight: f32 [N, K] (detached, on device); lora: (A [r_tot, K], B_full [N, r_tot]) f32
+        n, k = weight.shape
+        self.mode, self.n, self.k = mode, n, k
+        self.n_pad = _pad8(n)
+        perm = None
+        if swiglu_interleave:
+            half = n // 2
+            assert half % 128 == 0, "SwiGLU hidden size must be a multiple of 128"
+            idx = torch.arange(n, device=weight.device).view(2, half // 128, 128)
+            perm = idx.permute(1, 0, 2).reshape(-1)          # [gate blk0 | lin blk0 | gate blk1 | ...]
+            weight = weight[perm]
+            bias = bias[perm] if bias is not None else None
+        self.w = self._pack_matrix(weight, self.n_pad, w_side=True)
+        self.bias = None
+        if bias is not None:
+            self.bias = torch.zeros(self.n_pad, dtype=torch.float32, device=weight.device)
+            self.bias[:n].copy_(bias)
+        self.lora = None
+        if lora is not None:
+            a_mat, b_mat = lora                                # [r, K], [N, r] (alpha folded into B)
+            if perm is not None:
+                b_mat = b_mat[perm]
+            r = a_mat.shape[0]
+            if mode == "bf16":
+                r_pad = (r + 63) // 64 * 64                    # full 64-wide K blocks for the 2nd segment
+            else:
+                r_pad = _pad8(r)
+            a_pad = torch.zeros((r_pad, k), dtype=torch.float32, device=weight.device)
+            a_pad[:r].copy_(a_mat)
+            b_pad = torch.zeros((self.n_pad, r_pad), dtype=torch.float32, device=weight.device)
+            b_pad[:n, :r].copy_(b_mat)
+            self.lora = (PackedLinear(a_pad, None, mode), self._pack_matrix(b_pad, self.n_pad, w_side=True))
+
+    def _pack_matrix(self, mat, rows_pad, *, w_side):
+        rows, cols = mat.shape
+        mat = mat.contiguous()
+        if self.mode == "bf16":
+            return ops.cast_pad_bf16(mat, _pad8(cols), dst_rows=rows_pad)
+        return ops.split3_bf16(mat, _pad8(cols), w_side=w_side, dst_rows=rows_pad)
+
+    def _operand(self, x):
+        """Activation -> GEMM A operand in this mode."""
+        if self.mode == "bf16":
+            assert x.dtype == torch.bfloat16, "bf16 mode expects bf16 activations"
+            return x
+        assert x.dtype == torch.float32, "fp32 mode expects f32 activations"
+        return ops.split3_bf16(x, _pad8(x.shape[1]), w_side=False)
+
+    def __call__(self, x, *, act=ACT_NONE, scale=None, residual=None, out=None, out_dtype=None,
+                 patch_rows=0, out_rows=None):
+        adt = torch.bfloat16 if self.mode == "bf16" else torch.float32
+        a = self._operand(x)
+        a2 = w2 = None
+        if self.lora is not None:
+            t = self.lora[0](x, out_dtype=adt)                 # x.A^T  [M, r_pad]
+            a2, w2 = self.lora[0]._operand(t), self.lora[1]
+        return ops.gemm(a, self.w, self.bias, act=act, scale=scale, residual=residual, out=out,
+                        out_dtype=out_dtype or adt, a2=a2, w2=w2, patch_rows=patch_rows,
+                        out_rows=out_rows)
+
+
+def _lin_parts(mod):
+    """(weight, bias, loraA, alpha*loraB) of an nn.Linear or LoraLinear container (detached f32)."""
+    from .utils import LoraLinear
+    if isinstance(mod, LoraLinear):
+        w, b = mod.linear.weight.detach(), (mod.linear.bias.detach() if mod.linear.bias is not None else None)
+        return w.float(), (b.float() if b is not None else None), mod.lora_A.weight.detach().float(), \
+            mod.lora_B.weight.detach().float() * float(mod.alpha)
+    w = mod.weight.detach().float()
+    b = mod.bias.detach().float() if mod.bias is not None else None
+    return w, b, None, None
+
+
+def pack_linears(mods, mode, *, swiglu_interleave=False):
+    """Concatenate one or more (Lora)Linear containers along N into one PackedLinear.
+    LoRA pairs become one [sum r, K] A matrix and a block-diagonal B."""
+    parts = [_lin_parts(m) for m in mods]
+    w = torch.cat([p[0] for p in parts], dim=0)
+    b = None
+    if any(p[1] is not None for p in parts):
+        b = torch.cat([p[1] if p[1] is not None else torch.zeros(p[0].shape[0], device=w.device) for p in parts])
+    lora = None
+    if any(p[2] is not None for p in parts):
+        a_cat = torch.cat([p[2] for p in parts if p[2] is not None], dim=0)
+        b_full = torch.zeros((w.shape[0], a_cat.shape[0]), dtype=torch.float32, device=w.device)
+        r0 = n0 = 0
+        for p in parts:
+            n = p[0].shape[0]
+            if p[2] is not None:
+                r = p[2].shape[0]
+                b_full[n0:n0 + n, r0:r0 + r].copy_(p[3])
+                r0 += r
+            n0 += n
+        lora = (a_cat, b_full)
+    return PackedLinear(w, b, mode, lora=lora, swiglu_interleave=swiglu_interleave)
+
+
+def pack_raw(weight, bias, mode):
+    return PackedLinear(weight.detach().float(), bias.detach().float() if bias is not None else None, mode)
+
+
+def params_version(module):
+    """Cheap fingerprint of every parameter's storage + in-place version (optimizer steps,
+    load_state_dict and .to() all change it)."""
+    return tuple((p.data_ptr(), p._version) for p in module.parameters())
+
+
+def f32c(t):
+    return t.detach().float().contiguous()
+
+
+# ---------------------------------------------------------------------------
+# backbone (HF Dinov2Model restated as a kernel sequence)
+# ---------------------------------------------------------------------------
+class BackbonePack:
+    def __init__(self, bk, mode):
+        dino = bk.dino
+        emb = dino.embeddings
+        self.mode = mode
+        self.dim = bk.hidden_dim
+        self.heads = dino.num_heads
+        self.swiglu = dino.use_swiglu
+        d = self.dim
+        self.patch = pack_raw(emb.patch_embeddings.projection.weight.reshape(d, -1),
+                              emb.patch_embeddings.projection.bias, mode)
+        self.cls = f32c(emb.cls_token.reshape(d))
+        self.pos = f32c(emb.position_embeddings.reshape(-1, d))
+        self.pos_cache = {}
+        self.layers = []
+        for lyr in dino.encoder.layer:
+            att = lyr.attention
+            L = dict(
+                n1=(f32c(lyr.norm1.weight), f32c(lyr.norm1.bias)),
+                qkv=pack_linears([att.attention.query, att.attention.key, att.attention.value], mode),
+                proj=pack_linears([att.output.dense], mode),
+                ls1=f32c(lyr.layer_scale1.lambda1),
+                n2=(f32c(lyr.norm2.weight), f32c(lyr.norm2.bias)),
+                ls2=f32c(lyr.layer_scale2.lambda1),
+            )
+            if self.swiglu:
+                L["w_in"] = pack_linears([lyr.mlp.weights_in], mode, swiglu_interleave=True)
+                L["w_out"] = pack_linears([lyr.mlp.weights_out], mode)
+            else:
+                L["fc1"] = pack_linears([lyr.mlp.fc1], mode)
+                L["fc2"] = pack_linears([lyr.mlp.fc2], mode)
+            self.layers.append(L)
+        self.final_ln = (f32c(dino.layernorm.weight), f32c(dino.layernorm.bias))
+        self.proj = pack_linears([bk.projection], mode) if bk.projection is not None else None
+
+    def pos_for(self, h, w):
+        """HF interpolate_pos_encoding (modeling_dinov2.py:57-95): identity at the native square
+        size, else bicubic resize in fp32 -- input independent, so cached per (H, W)."""
+        gh, gw = h // 14, w // 14
+        n_pos = self.pos.shape[0] - 1
+        if gh * gw == n_pos and h == w:
+            return self.pos
+        key = (gh, gw)
+        if key not in self.pos_cache:
+            g0 = int(n_pos ** 0.5)
+            self.pos_cache[key] = ops.pos_resize_bicubic(self.pos, g0, gh, gw)
+        return self.pos_cache[key]
+
+
+def backbone_forward(pack: BackbonePack, pixel_values):
+    """-> memory [B*N, hidden] in the activation dtype of the mode, and (B, N)."""
+    mode = pack.mode
+    adt = torch.bfloat16 if mode == "bf16" else torch.float32
+    if pixel_values.dim() != 4:
+        raise ValueError(f"pixel_values must be [B, 3, H, W], got {tuple(pixel_values.shape)}")
+    px = pixel_values.detach()
+    if px.dtype != torch.float32 or not px.is_contiguous():
+        px = px.float().contiguous()
+    b, _, h, w = px.shape
+    gh, gw = h // 14, w // 14
+    p, n, d = gh * gw, gh * gw + 1, pack.dim
+    m = b * n
+    pos = pack.pos_for(h, w)
+    x = torch.empty((m, d), dtype=torch.float32, device=px.device)       # fp32 residual stream
+    patches = ops.patchify14(px, 592, cls=pack.cls, pos=pos, tokens=x)
+    if mode == "fp32":
+        # fp32 mode: im2col once more in full precision (bf16 patches would cost 3 digits)
+        patches = _patchify_f32(px, gh, gw)
+        pack.patch(patches, residual=pos, out=x, patch_rows=p)
+    else:
+        ops.gemm(patches, pack.patch.w, pack.patch.bias, residual=pos, out=x, patch_rows=p)
+    scale = 1.0 / math.sqrt(64.0)
+    for L in pack.layers:
+        hN = ops.layernorm(x, *L["n1"], 1e-6, out_dtype=adt)
+        qkv = L["qkv"](hN)                                                  # [M, 3D]
+        if mode == "bf16":
+            ctx = ops.fmha(qkv, b, n, pack.heads, q_off=0, k_off=d, v_off=2 * d, scale=scale)
+        else:
+            ctx = ops.mha_small(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], b, n, n, pack.heads, 64, scale)
+        L["proj"](ctx, scale=L["ls1"], residual=x, out=x)                   # x += ls1 * (ctx Wo^T + b)
+        hN = ops.layernorm(x, *L["n2"], 1e-6, out_dtype=adt)
+        if pack.swiglu:
+            a = L["w_in"](hN, act=ACT_SWIGLU)
+            L["w_out"](a, scale=L["ls2"], residual=x, out=x)
+        else:
+            a = L["fc1"](hN, act=ACT_GELU_ERF)
+            L["fc2"](a, scale=L["ls2"], residual=x, out=x)
+    mem = ops.layernorm(x, *pack.final_ln, 1e-6, out_dtype=adt)
+    if pack.proj is not None:
+        mem = pack.proj(mem)
+    return mem, b, n
+
+
+def _patchify_f32(px, gh, gw):
+    """fp32-mode im2col: pure data movement (a strided view copy), no arithmetic."""
+    b = px.shape[0]
+    v = px[:, :, :gh * 14, :gw * 14].reshape(b, 3, gh, 14, gw, 14).permute(0, 2, 4, 1, 3, 5)
+    return v.reshape(b * gh * gw, 588).contiguous()
+
+
+# ---------------------------------------------------------------------------
+# decoder
+# ---------------------------------------------------------------------------
+def grid_shape(hw: int):
+    """reference deformable_attention.py:241-256: largest factor pair of the token count,
+    CLS token included (257 -> (1, 257), 1370 -> (10, 137))."""
+    s = int(hw ** 0.5)
+    if s * s == hw:
+        return s, s
+    for i in range(s, 0, -1):
+        if hw % i == 0:
+            return i, hw // i
+    return s, s
+
+
+class DecoderPack:
+    def __init__(self, dec, mode):
+        self.mode = mode
+        self.q = dec.num_queries
+        self.h = dec.hidden_dim
+        self.heads = dec.nheads
+        self.deformable = dec.use_deformable
+        self.points = dec.n_points
+        self.query = f32c(dec.query_embed.weight)
+        self.layers = []
+        layers = list(dec.decoder.layers)
+        for lyr in layers:
+            sa = lyr.self_attn
+            L = dict(
+                sa_in=pack_raw(sa.in_proj_weight, sa.in_proj_bias, mode),
+                sa_out=pack_linears([sa.out_proj], mode),
+                n1=(f32c(lyr.norm1.weight), f32c(lyr.norm1.bias)),
+                n2=(f32c(lyr.norm2.weight), f32c(lyr.norm2.bias)),
+                n3=(f32c(lyr.norm3.weight), f32c(lyr.norm3.bias)),
+                l1=pack_linears([lyr.linear1], mode),
+                l2=pack_linears([lyr.linear2], mode),
+            )
+            if self.deformable:
+                ca = lyr.cross_attn
+                # one GEMM for the three projections of the query: [offsets | logits | ref point]
+                L["qproj"] = pack_linears([ca.sampling_offsets, ca.attention_weights,
+                                           lyr.reference_points_proj], mode)
+                L["value"] = pack_linears([ca.value_proj], mode)
+                L["out"] = pack_linears([ca.output_proj], mode)
+            else:
+                ca = lyr.multihead_attn
+                hd = self.h
+                L["ca_q"] = pack_raw(ca.in_proj_weight[:hd], ca.in_proj_bias[:hd], mode)
+                L["ca_kv"] = pack_raw(ca.in_proj_weight[hd:], ca.in_proj_bias[hd:], mode)
+                L["ca_out"] = pack_linears([ca.out_proj], mode)
+            self.layers.append(L)
+            if self.deformable:
+                # the reference stacks ONE layer object n times (deformable_attention.py:284):
+                # every entry is the same module, pack it once.
+                self.layers = [L] * len(layers)
+                break
+        self.cls = pack_linears([dec.class_embed], mode)
+        self.box0 = pack_linears([dec.bbox_embed.mlp[0]], mode)
+        self.box1 = pack_linears([dec.bbox_embed.mlp[2]], mode)
+        self.num_classes = dec.class_embed.out_features
+
+
+def _post_norm(x_f32, ln, adt):
+    """LayerNorm of the (already residual-added) fp32 stream; returns (f32, activation-dtype)."""
+    if adt == torch.float32:
+        y = ops.layernorm(x_f32, *ln, 1e-5, out_dtype=torch.float32)
+        return y, y
+    y32, y16 = ops.layernorm(x_f32, *ln, 1e-5, out_dtype=torch.float32, also_other=True)
+    return y32, y16
+
+
+def decoder_forward(pack: DecoderPack, memory, b, n):
+    """memory [B*N, h] (activation dtype) -> (pred_logits [B,Q,C] f32, pred_boxes [B,Q,4] f32)."""
+    mode = pack.mode
+    adt = torch.bfloat16 if mode == "bf16" else torch.float32
+    q, hd, heads = pack.q, pack.h, pack.heads
+    dh = hd // heads
+    scale = 1.0 / math.sqrt(dh)
+    tgt32, tgt16 = ops.broadcast_rows(pack.query, b, want_bf16=(adt == torch.bfloat16))
+    tgt = tgt16 if adt == torch.bfloat16 else tgt32
+    value = None
+    if pack.deformable:
+        if n != memory.shape[0] // b:
+            raise ValueError("memory shape mismatch")
+        gh, gw = grid_shape(n)
+        if gh * gw != n:
+            # reference deformable_attention.py:76-82
+            raise ValueError(f"Cannot reshape input of size {n} into a square feature map")
+    for L in pack.layers:
+        # --- self attention (nn.MultiheadAttention, deformable_attention.py:232-235) ---
+        qkv = L["sa_in"](tgt)
+        ctx = ops.mha_small(qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:], b, q, q, heads, dh, scale)
+        x = L["sa_out"](ctx, residual=tgt32, out_dtype=torch.float32)
+        tgt32, tgt = _post_norm(x, L["n1"], adt)
+        # --- cross attention ---
+        if pack.deformable:
+            if value is None:           # shared layer weights: value_proj(memory) is layer-invariant
+                value = L["value"](memory)
+            hp = heads * pack.points
+            qp = L["qproj"](tgt, out_dtype=torch.float32)      # [B*Q, pad8(3*hp + 2)]
+            samp = ops.deform_sample(value, qp[:, 3 * hp:3 * hp + 2], qp[:, :2 * hp], qp[:, 2 * hp:3 * hp],
+                                     b, q, heads, pack.points, dh, gh, gw, ref_is_logit=True, out_dtype=adt)
+            x = L["out"](samp, residual=tgt32, out_dtype=torch.float32)
+        else:
+            cq = L["ca_q"](tgt)
+            kv = L["ca_kv"](memory)                            # [B*N, 2h]
+            ctx = ops.mha_small(cq, kv[:, :hd], kv[:, hd:], b, q, n, heads, dh, scale)
+            x = L["ca_out"](ctx, residual=tgt32, out_dtype=torch.float32)
+        tgt32, tgt = _post_norm(x, L["n2"], adt)
+        # --- FFN ---
+        a = L["l1"](tgt, act=ACT_RELU)
+        x = L["l2"](a, residual=tgt32, out_dtype=torch.float32)
+        tgt32, tgt = _post_norm(x, L["n3"], adt)
+    logits = pack.cls(tgt, out_dtype=torch.float32)
+    hid = pack.box0(tgt, act=ACT_RELU)
+    box = pack.box1(hid, out_dtype=torch.float32)
+    pred_logits = ops.rowcopy(logits, pack.num_classes).view(b, q, pack.num_classes)
+    pred_boxes = ops.rowcopy(box, 4, sigmoid=True).view(b, q, 4)
+    return pred_logits, pred_boxes

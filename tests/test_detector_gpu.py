@@ -1,0 +1,78 @@
+"""GPU parity of the detector forward: libdod path vs the CPU oracle and the reference's own
+outputs (tests/golden) on identical synthetic weights and images.
+
+Tolerances (BASELINE.json north_star): fp32 mode 1e-4 relative, bf16 mode 2e-2 relative
+(relative to the largest magnitude of the compared tensor)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import build_product_model, golden, manifest, oracle_forward, rel_err, synth
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["c1_small_deform", "c1_small_std", "small_nonsquare", "giant3_swiglu", "base_518", "large_proj_std"]
+
+
+def _run(case, precision):
+    man = manifest()[case]
+    model, sd, kw = build_product_model(case, device="cuda")
+    model.precision = precision
+    x = synth.make_images(man["batch"], *man["hw"], seed=man["image_seed"])
+    with torch.no_grad():
+        out = model(x.cuda())
+    torch.cuda.synchronize()
+    return out, sd, kw, x
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_fp32_mode_matches_reference_golden(case):
+    out, sd, kw, x = _run(case, "fp32")
+    g = golden("detector_" + case)
+    assert out["pred_logits"].shape == g["pred_logits"].shape and out["pred_logits"].dtype == torch.float32
+    assert rel_err(out["pred_logits"], torch.from_numpy(g["pred_logits"])) < 1e-4
+    assert rel_err(out["pred_boxes"], torch.from_numpy(g["pred_boxes"])) < 1e-4
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_bf16_mode_matches_reference_golden(case):
+    out, sd, kw, x = _run(case, "bf16")
+    g = golden("detector_" + case)
+    assert rel_err(out["pred_logits"], torch.from_numpy(g["pred_logits"])) < 2e-2
+    assert rel_err(out["pred_boxes"], torch.from_numpy(g["pred_boxes"])) < 2e-2
+    b = out["pred_boxes"]
+    assert (b > 0).all() and (b < 1).all()
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_backbone_memory_matches_oracle(precision, tol):
+    """backbone.forward (reference dinov2_backbone.py:58-67) incl. LoRA on the last two blocks."""
+    from helpers import detector_oracle
+    case = "c1_small_std"
+    man = manifest()[case]
+    model, sd, kw = build_product_model(case, device="cuda")
+    model.precision = precision
+    x = synth.make_images(man["batch"], *man["hw"], seed=man["image_seed"])
+    with torch.no_grad():
+        mem = model.backbone(x.cuda())
+    ref = detector_oracle.backbone(sd, x, "small", kw["lora_alpha"])
+    assert mem.shape == ref.shape
+    assert rel_err(mem, ref) < tol
+
+
+def test_weights_update_invalidates_pack():
+    """In-place parameter updates (optimizer.step / load_state_dict) must be picked up."""
+    case = "c1_small_std"
+    model, sd, kw = build_product_model(case, device="cuda")
+    x = synth.make_images(1, 224, 224, seed=5).cuda()
+    with torch.no_grad():
+        a = model(x)["pred_logits"].clone()
+        model.decoder.class_embed.bias.add_(1.0)
+        b = model(x)["pred_logits"]
+    assert torch.allclose(b - a, torch.ones_like(a), atol=2e-2)
+
+
+def test_channel_mismatch_raises_value_error():
+    model, _, _ = build_product_model("c1_small_std", device="cuda")
+    with torch.no_grad(), pytest.raises(ValueError):
+        model(torch.rand(1, 4, 224, 224).cuda())
