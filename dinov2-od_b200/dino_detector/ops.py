@@ -14,6 +14,42 @@ from ._dod import (ACT_GELU_ERF, ACT_NONE, ACT_RELU, ACT_SWIGLU, DOD_BF16, DOD_F
 
 _DT = {torch.bfloat16: DOD_BF16, torch.float32: DOD_F32}
 
+# Optional per-launch timing (bench.py): when a list is installed, the tensor-core ops bracket
+# their launch with CUDA events on the launching stream and append (kind, flops, start, end).
+_profile = None
+
+
+def profile_begin():
+    global _profile
+    _profile = []
+
+
+def profile_end():
+    """-> {kind: (launches, total_flops, total_ms)}; call after torch.cuda.synchronize()."""
+    global _profile
+    rec, _profile = _profile or [], None
+    out = {}
+    for kind, flops, e0, e1 in rec:
+        n, f, t = out.get(kind, (0, 0.0, 0.0))
+        out[kind] = (n + 1, f + flops, t + e0.elapsed_time(e1))
+    return out
+
+
+class _Timed:
+    def __init__(self, kind, flops):
+        self.kind, self.flops = kind, flops
+
+    def __enter__(self):
+        if _profile is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if _profile is not None and exc[0] is None:
+            self.e1.record()
+            _profile.append((self.kind, self.flops, self.e0, self.e1))
+
 
 def _stream(t: torch.Tensor) -> int:
     if not t.is_cuda:
@@ -55,7 +91,9 @@ def gemm(a, w, bias=None, *, act=ACT_NONE, scale=None, residual=None, out=None,
         assert scale.dtype == torch.float32 and scale.numel() >= n
     if residual is not None:
         assert residual.dtype == torch.float32
-    _dod.call("dod_gemm_bf16", _stream(a), **kw)
+    k_tot = k + (a2.shape[1] if a2 is not None else 0)
+    with _Timed("gemm", 2.0 * m * n * k_tot):
+        _dod.call("dod_gemm_bf16", _stream(a), **kw)
     return out
 
 
@@ -69,8 +107,10 @@ def layernorm(x, gamma, beta, eps, *, out_dtype=torch.bfloat16, also_other=False
     if also_other:
         other = torch.float32 if y.dtype == torch.bfloat16 else torch.bfloat16
         y2 = torch.empty((rows, d), dtype=other, device=x.device)
-    _dod.call("dod_layernorm", _stream(x), x=x, x_dtype=_DT[x.dtype], gamma=gamma, beta=beta, y=y,
-              y_dtype=_DT[y.dtype], y2=y2, rows=rows, d=d, ldx=ldx, ldy=_rowmajor(y, "y"), eps=eps)
+    nbytes = rows * d * (x.element_size() + y.element_size() + (y2.element_size() if y2 is not None else 0))
+    with _Timed("layernorm", float(nbytes)):
+        _dod.call("dod_layernorm", _stream(x), x=x, x_dtype=_DT[x.dtype], gamma=gamma, beta=beta, y=y,
+                  y_dtype=_DT[y.dtype], y2=y2, rows=rows, d=d, ldx=ldx, ldy=_rowmajor(y, "y"), eps=eps)
     return (y, y2) if also_other else y
 
 
@@ -107,8 +147,9 @@ def fmha(qkv, batch, seq, heads, *, q_off, k_off, v_off, scale, out=None):
     assert qkv.shape[0] == batch * seq
     if out is None:
         out = torch.empty((batch * seq, heads * 64), dtype=torch.bfloat16, device=qkv.device)
-    _dod.call("dod_fmha_fwd", _stream(qkv), qkv=qkv, ctx=out, batch=batch, seq=seq, heads=heads,
-              ld=ld, ldo=_rowmajor(out, "out"), q_off=q_off, k_off=k_off, v_off=v_off, scale=scale)
+    with _Timed("fmha", 4.0 * batch * heads * seq * seq * 64):
+        _dod.call("dod_fmha_fwd", _stream(qkv), qkv=qkv, ctx=out, batch=batch, seq=seq, heads=heads,
+                  ld=ld, ldo=_rowmajor(out, "out"), q_off=q_off, k_off=k_off, v_off=v_off, scale=scale)
     return out
 
 
