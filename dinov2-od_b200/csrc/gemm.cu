@@ -6,14 +6,24 @@
 //   * A and W are both K-major (row-major activations, nn.Linear weights), so
 //     both operands are TMA-loaded as [rows x 64] bf16 boxes with the 128-byte
 //     swizzle and consumed by tcgen05.mma straight from shared memory.
-//   * CTA tile 128 x BN (BN = 256 / 128 / 64), BK = 64; 4..8 smem stages.
-//   * warp 0: TMA producer, warp 1: MMA issuer (one lane), warps 2..5: epilogue
-//     (TMEM -> registers -> fused bias/act/LayerScale/residual -> global).
+//   * CTA tile 128 x BN (BN = 256 / 128 / 64), BK = 64; 3..6 smem stages.
+//   * warp 0: TMA producer, warp 1: MMA issuer (one lane), warps 2..9: epilogue.
 //   * two TMEM accumulator stages, so the epilogue of tile i overlaps the
 //     mainloop of tile i+1; grid = min(tiles, #SM) persistent CTAs; tiles are
 //     walked N-fastest so CTAs running together share A rows through L2.
 //   * the optional second K segment (LoRA: A2 = x.A^T, W2 = alpha*B) is simply
 //     more k-blocks accumulated into the same TMEM tile.
+//   * epilogue: each TMEM lane quadrant (32 rows) is served by TWO warps that
+//     alternate over 64-byte-wide column chunks.  A chunk goes TMEM -> registers
+//     (one row per thread) -> bias / act / LayerScale / +residual -> 64B-swizzled
+//     shared memory -> TMA store, so global writes are full coalesced lines; the
+//     fp32 residual chunk arrives the same way through a TMA load that is
+//     prefetched one chunk ahead.  (The first version stored rows straight from
+//     registers: 32 lanes x 16 B scattered over 32 rows per instruction made the
+//     K=768 GEMMs epilogue-bound at 16-43 % tensor-pipe utilisation, see
+//     profiles/r01_summary.md.)
+//   * the patch-embedding row map (patch_rows > 0) cannot be expressed as a TMA
+//     box and keeps the direct register -> global path (0.4 % of the FLOPs).
 //
 // Replaces cuBLAS calls behind nn.Linear / Conv2d in the reference path (see
 // include/dod.h for file:line citations).
@@ -27,7 +37,9 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + kEpiWarps * 32;
+constexpr int kChunkBytes = 32 * 64;  // one epilogue chunk buffer: 32 rows x 64 B
 
 struct GemmParams {
   int M, N, K1blocks, K2blocks;
@@ -41,29 +53,284 @@ struct GemmParams {
   int act;
   int out_f32;
   int patch_rows;
+  int direct;  // 1: register -> global epilogue (patch rows / shapes TMA cannot store)
 };
 
-template <int BN>
+template <int BN, bool RES>
 struct SmemLayout {
   static constexpr int kStageA = BM * BK * 2;
   static constexpr int kStageB = BN * BK * 2;
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int kBarBytes = 1024;
-  static constexpr int kTotal = kStages * kStage + kBarBytes + 1024 /*align slack*/;
+  static constexpr int kStages = (BN == 256) ? (RES ? 3 : 4) : (BN == 128 ? 5 : 6);
+  static constexpr int kEpiBufs = RES ? 4 : 2;  // per warp: 2 out (+ 2 residual)
+  static constexpr int kEpiBytes = kEpiWarps * kEpiBufs * kChunkBytes;
+  static constexpr int kBarBytes = 512;
+  static constexpr int kTotal = kStages * kStage + kEpiBytes + kBarBytes + 1024 /*align slack*/;
+  static_assert(kTotal <= 232448, "shared memory budget exceeded");
 };
 
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
+// erf(z) ~ z * P(z^2) on |z| <= 3 (clamped beyond: 1 - erf(3) = 2.2e-5); max abs error 2.7e-5 in
+// fp32 Horner form.  Used only when the result is rounded to bf16 (ulp 2^-9): 8 FMAs instead of
+// erff's ~25 instructions, which kept the fc1 epilogue above the MMA time per tile.
+__device__ __forceinline__ float gelu_erf_bf16(float x) {
+  const float z = fminf(fmaxf(x * 0.70710678118654752440f, -3.0f), 3.0f);
+  const float s = z * z;
+  float p = 4.074217297e-08f;
+  p = fmaf(p, s, -1.944825111e-06f);
+  p = fmaf(p, s, 4.106055886e-05f);
+  p = fmaf(p, s, -5.110371310e-04f);
+  p = fmaf(p, s, 4.235428557e-03f);
+  p = fmaf(p, s, -2.510286399e-02f);
+  p = fmaf(p, s, 1.110793386e-01f);
+  p = fmaf(p, s, -3.753148772e-01f);
+  p = fmaf(p, s, 1.128268426e+00f);
+  const float hx = 0.5f * x;
+  return fmaf(hx, z * p, hx);
+}
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
+template <int COLS>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[COLS]) {
+  if constexpr (COLS == 16) tmem_ld_32x16(taddr, v);
+  else tmem_ld_32x32(taddr, v);
+}
+
+// byte offset of logical 16-byte chunk j of row r inside a 64B-swizzled [32 x 64 B] buffer
+__device__ __forceinline__ uint32_t sw64(int r, int j) { return r * 64 + ((j ^ ((r >> 1) & 3)) << 4); }
+
+// Epilogue of one tile through shared memory, in chunks of COLS output columns
+// (16 fp32 or 32 bf16 = 64 bytes per row).
+template <int BN, bool RES, bool OUT_F32>
+__device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUtensorMap* tm_out,
+                                                  const CUtensorMap* tm_res, uint32_t t_row, int mb,
+                                                  int nb, int quad, int half, int lane,
+                                                  uint8_t* out_buf, uint8_t* res_buf,
+                                                  uint64_t* res_full, uint32_t& out_cnt,
+                                                  uint32_t& res_issue, uint32_t& res_wait,
+                                                  uint64_t* tempty_bar) {
+  constexpr int COLS = OUT_F32 ? 16 : 32;
+  const bool swiglu = p.act == DOD_ACT_SWIGLU;
+  const int width = swiglu ? BN / 2 : BN;  // output columns of this tile
+  const int nch = width / COLS;
+  const int row0 = mb * BM + quad * 32;
+  const int col_base = nb * width;
+  const int n_out = swiglu ? p.N / 2 : p.N;
+
+  if constexpr (RES) {
+    if (half < nch) {
+      if (lane == 0) {
+        uint64_t* bar = &res_full[res_issue & 1];
+        mbar_expect_tx(bar, kChunkBytes);
+        tma_load_2d(res_buf + (res_issue & 1) * kChunkBytes, tm_res, bar, col_base + half * COLS, row0);
+      }
+      ++res_issue;
+    }
+  }
+
+#pragma unroll 1
+  for (int c = half; c < nch; c += 2) {
+    const int n0 = col_base + c * COLS;  // first output column of the chunk
+    if constexpr (RES) {
+      if (c + 2 < nch) {
+        if (lane == 0) {
+          uint64_t* bar = &res_full[res_issue & 1];
+          mbar_expect_tx(bar, kChunkBytes);
+          tma_load_2d(res_buf + (res_issue & 1) * kChunkBytes, tm_res, bar, n0 + 2 * COLS, row0);
+        }
+        ++res_issue;
+      }
+    }
+    uint32_t v[COLS];
+    uint32_t u[COLS];
+    tmem_ld_cols<COLS>(t_row + c * COLS, v);
+    if (swiglu) tmem_ld_cols<COLS>(t_row + BN / 2 + c * COLS, u);
+    tmem_ld_wait();
+    if (c + 2 >= nch) {
+      // this warp has read its share of the accumulator: hand the TMEM stage back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar);
+    }
+    float r[COLS];
+#pragma unroll
+    for (int j = 0; j < COLS; ++j) r[j] = __uint_as_float(v[j]);
+    const bool in_range = n0 < n_out;  // chunk entirely outside N: nothing to compute or store
+    if (swiglu) {
+      // accumulator columns [0, BN/2) are gates, [BN/2, BN) the linear halves (interleaved W rows)
+      const int nw = nb * BN + c * COLS;
+#pragma unroll
+      for (int j = 0; j < COLS; ++j) {
+        float gv = r[j], uv = __uint_as_float(u[j]);
+        if (p.bias) {
+          gv += __ldg(p.bias + nw + j);
+          uv += __ldg(p.bias + nw + BN / 2 + j);
+        }
+        r[j] = silu(gv) * uv;
+      }
+    } else if (in_range) {
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < COLS; j += 4) {
+          if (n0 + j < p.N) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+            r[j] += b.x; r[j + 1] += b.y; r[j + 2] += b.z; r[j + 3] += b.w;
+          }
+        }
+      }
+      if (p.act == DOD_ACT_GELU_ERF) {
+#pragma unroll
+        for (int j = 0; j < COLS; ++j) r[j] = OUT_F32 ? gelu_erf(r[j]) : gelu_erf_bf16(r[j]);
+      } else if (p.act == DOD_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < COLS; ++j) r[j] = fmaxf(r[j], 0.0f);
+      }
+      if (p.scale) {
+#pragma unroll
+        for (int j = 0; j < COLS; j += 4) {
+          if (n0 + j < p.N) {
+            const float4 s = __ldg(reinterpret_cast<const float4*>(p.scale + n0 + j));
+            r[j] *= s.x; r[j + 1] *= s.y; r[j + 2] *= s.z; r[j + 3] *= s.w;
+          }
+        }
+      }
+    }
+    if constexpr (RES) {
+      mbar_wait(&res_full[res_wait & 1], (res_wait >> 1) & 1);
+      const uint8_t* rb = res_buf + (res_wait & 1) * kChunkBytes;
+      ++res_wait;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 q = *reinterpret_cast<const float4*>(rb + sw64(lane, j));
+        r[4 * j] += q.x; r[4 * j + 1] += q.y; r[4 * j + 2] += q.z; r[4 * j + 3] += q.w;
+      }
+    }
+    // the store issued two chunks ago read this buffer: wait until it has been drained
+    if (lane == 0) tma_store_wait_read<1>();
+    __syncwarp();
+    uint8_t* ob = out_buf + (out_cnt & 1) * kChunkBytes;
+    ++out_cnt;
+    if constexpr (OUT_F32) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<float4*>(ob + sw64(lane, j)) =
+            make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 q;
+        q.x = pack_bf16x2(r[8 * j], r[8 * j + 1]);
+        q.y = pack_bf16x2(r[8 * j + 2], r[8 * j + 3]);
+        q.z = pack_bf16x2(r[8 * j + 4], r[8 * j + 5]);
+        q.w = pack_bf16x2(r[8 * j + 6], r[8 * j + 7]);
+        *reinterpret_cast<uint4*>(ob + sw64(lane, j)) = q;
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0 && in_range && row0 < p.M) {
+      tma_store_2d(tm_out, ob, n0, row0);
+      tma_store_commit();
+    }
+  }
+}
+
+// Register -> global epilogue (one row per thread).  Kept for the patch-embedding row map.
 template <int BN>
+__device__ __forceinline__ void epilogue_tile_direct(const GemmParams& p, uint32_t t_row, int mb,
+                                                     int nb, int quad, int half, int lane,
+                                                     uint64_t* tempty_bar) {
+  const int m = mb * BM + quad * 32 + lane;
+  const bool row_ok = m < p.M;
+  int64_t out_row = m, res_row = m;
+  if (p.patch_rows > 0) {
+    out_row = int64_t(m) + m / p.patch_rows + 1;
+    res_row = 1 + m % p.patch_rows;
+  }
+  constexpr int NCH = BN / 32;
+#pragma unroll 1
+  for (int c = half; c < NCH; c += 2) {
+    uint32_t v[32];
+    tmem_ld_32x32(t_row + c * 32, v);
+    tmem_ld_wait();
+    if (c + 2 >= NCH) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar);
+    }
+    const int n0 = nb * BN + c * 32;
+    if (!row_ok || n0 >= p.N) continue;
+    float r[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]);
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        if (n0 + j < p.N) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+          r[j] += b.x; r[j + 1] += b.y; r[j + 2] += b.z; r[j + 3] += b.w;
+        }
+      }
+    }
+    if (p.act == DOD_ACT_GELU_ERF) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = gelu_erf(r[j]);
+    } else if (p.act == DOD_ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = fmaxf(r[j], 0.0f);
+    }
+    if (p.scale) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        if (n0 + j < p.N) {
+          const float4 s = __ldg(reinterpret_cast<const float4*>(p.scale + n0 + j));
+          r[j] *= s.x; r[j + 1] *= s.y; r[j + 2] *= s.z; r[j + 3] *= s.w;
+        }
+      }
+    }
+    if (p.residual) {
+      const float* rp = p.residual + res_row * p.ldr + n0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        if (n0 + j < p.N) {
+          const float4 q = *reinterpret_cast<const float4*>(rp + j);
+          r[j] += q.x; r[j + 1] += q.y; r[j + 2] += q.z; r[j + 3] += q.w;
+        }
+      }
+    }
+    if (p.out_f32) {
+      float* o = reinterpret_cast<float*>(p.out) + out_row * p.ldo + n0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        if (n0 + j < p.N)
+          *reinterpret_cast<float4*>(o + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+      }
+    } else {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldo + n0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        if (n0 + j < p.N) {
+          uint4 q;
+          q.x = pack_bf16x2(r[j], r[j + 1]);
+          q.y = pack_bf16x2(r[j + 2], r[j + 3]);
+          q.z = pack_bf16x2(r[j + 4], r[j + 5]);
+          q.w = pack_bf16x2(r[j + 6], r[j + 7]);
+          *reinterpret_cast<uint4*>(o + j) = q;
+        }
+      }
+    }
+  }
+}
+
+template <int BN, bool RES>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
             const __grid_constant__ CUtensorMap tm_a2, const __grid_constant__ CUtensorMap tm_w2,
+            const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_res,
             const GemmParams p) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, RES>;
   constexpr int kStages = L::kStages;
   constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : 2 * BN;  // two accumulator stages
 
@@ -71,12 +338,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
   uint8_t* stage_base = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * L::kStage);
-  uint64_t* full = bars;                    // [kStages]
-  uint64_t* empty = bars + kStages;         // [kStages]
-  uint64_t* tfull = bars + 2 * kStages;     // [2]
-  uint64_t* tempty = bars + 2 * kStages + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint8_t* epi_base = smem + kStages * L::kStage;  // 1 KB aligned (stage sizes are multiples of 1 KB)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_base + L::kEpiBytes);
+  uint64_t* full = bars;                        // [kStages]
+  uint64_t* empty = bars + kStages;             // [kStages]
+  uint64_t* tfull = bars + 2 * kStages;         // [2]
+  uint64_t* tempty = bars + 2 * kStages + 2;    // [2]
+  uint64_t* res_bars = bars + 2 * kStages + 4;  // [kEpiWarps][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bars + 2 * kEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -88,14 +357,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       prefetch_tmap(&tm_a2);
       prefetch_tmap(&tm_w2);
     }
+    if (!p.direct) prefetch_tmap(&tm_out);
+    if (RES) prefetch_tmap(&tm_res);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 4);
+      mbar_init(&tempty[s], kEpiWarps);
     }
+    for (int s = 0; s < 2 * kEpiWarps; ++s) mbar_init(&res_bars[s], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_slot);
@@ -163,8 +435,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // ===================== epilogue (warps 2..9) =====================
+    const int quad = warp & 3;         // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;  // which of the quadrant's two warps
+    const int ew = warp - 2;
+    uint8_t* out_buf = epi_base + ew * L::kEpiBufs * kChunkBytes;
+    uint8_t* res_buf = out_buf + 2 * kChunkBytes;
+    uint64_t* res_full = res_bars + 2 * ew;
+    uint32_t out_cnt = 0, res_issue = 0, res_wait = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int mb = tile / p.tiles_n, nb = tile % p.tiles_n;
@@ -172,139 +450,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       const uint32_t acc_ph = (it >> 1) & 1;
       mbar_wait(&tfull[acc], acc_ph);
       tc_fence_after();
-      const int m = mb * BM + quad * 32 + lane;
-      const bool row_ok = m < p.M;
-      int64_t out_row = m, res_row = m;
-      if (p.patch_rows > 0) {
-        out_row = int64_t(m) + m / p.patch_rows + 1;
-        res_row = 1 + m % p.patch_rows;
-      }
       const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
-
-      if (p.act == DOD_ACT_SWIGLU) {
-        // columns [0,BN/2) of the tile are gates, [BN/2,BN) the linear halves.
-        constexpr int H = BN / 2;
-#pragma unroll 1
-        for (int c = 0; c < H / 32; ++c) {
-          uint32_t g[32], u[32];
-          tmem_ld_32x32(t_row + c * 32, g);
-          tmem_ld_32x32(t_row + H + c * 32, u);
-          tmem_ld_wait();
-          if (c == H / 32 - 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[acc]);
-          }
-          const int n_in = nb * BN + c * 32;           // gate column in W space
-          const int n_out = nb * H + c * 32;           // output column
-          if (row_ok && n_out < p.N / 2) {
-            float r[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float gv = __uint_as_float(g[j]), uv = __uint_as_float(u[j]);
-              if (p.bias) {
-                gv += __ldg(p.bias + n_in + j);
-                uv += __ldg(p.bias + n_in + H + j);
-              }
-              r[j] = silu(gv) * uv;
-            }
-            if (p.out_f32) {
-              float* o = reinterpret_cast<float*>(p.out) + out_row * p.ldo + n_out;
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(o + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-            } else {
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldo + n_out;
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 v;
-                v.x = pack_bf16x2(r[j], r[j + 1]);
-                v.y = pack_bf16x2(r[j + 2], r[j + 3]);
-                v.z = pack_bf16x2(r[j + 4], r[j + 5]);
-                v.w = pack_bf16x2(r[j + 6], r[j + 7]);
-                *reinterpret_cast<uint4*>(o + j) = v;
-              }
-            }
-          }
-        }
-        continue;
-      }
-
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_row + c * 32, v);
-        tmem_ld_wait();
-        if (c == BN / 32 - 1) {
-          // accumulator fully read: hand the TMEM stage back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty[acc]);
-        }
-        const int n0 = nb * BN + c * 32;
-        if (!row_ok || n0 >= p.N) continue;
-        float r[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(v[j]);
-        const bool full_chunk = (n0 + 32 <= p.N);
-        if (p.bias) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (full_chunk || n0 + j < p.N) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-              r[j] += b.x; r[j + 1] += b.y; r[j + 2] += b.z; r[j + 3] += b.w;
-            }
-          }
-        }
-        if (p.act == DOD_ACT_GELU_ERF) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = gelu_erf(r[j]);
-        } else if (p.act == DOD_ACT_RELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = fmaxf(r[j], 0.0f);
-        }
-        if (p.scale) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (full_chunk || n0 + j < p.N) {
-              const float4 s = __ldg(reinterpret_cast<const float4*>(p.scale + n0 + j));
-              r[j] *= s.x; r[j + 1] *= s.y; r[j + 2] *= s.z; r[j + 3] *= s.w;
-            }
-          }
-        }
-        if (p.residual) {
-          const float* rp = reinterpret_cast<const float*>(p.residual) + res_row * p.ldr + n0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (full_chunk || n0 + j < p.N) {
-              const float4 q = *reinterpret_cast<const float4*>(rp + j);
-              r[j] += q.x; r[j + 1] += q.y; r[j + 2] += q.z; r[j + 3] += q.w;
-            }
-          }
-        }
-        if (p.out_f32) {
-          float* o = reinterpret_cast<float*>(p.out) + out_row * p.ldo + n0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (full_chunk || n0 + j < p.N)
-              *reinterpret_cast<float4*>(o + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-          }
-        } else {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + out_row * p.ldo + n0;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (full_chunk || n0 + j < p.N) {
-              uint4 q;
-              q.x = pack_bf16x2(r[j], r[j + 1]);
-              q.y = pack_bf16x2(r[j + 2], r[j + 3]);
-              q.z = pack_bf16x2(r[j + 4], r[j + 5]);
-              q.w = pack_bf16x2(r[j + 6], r[j + 7]);
-              *reinterpret_cast<uint4*>(o + j) = q;
-            }
-          }
-        }
+      if (p.direct) {
+        epilogue_tile_direct<BN>(p, t_row, mb, nb, quad, half, lane, &tempty[acc]);
+      } else if (p.out_f32) {
+        epilogue_tile_tma<BN, RES, true>(p, &tm_out, &tm_res, t_row, mb, nb, quad, half, lane, out_buf,
+                                         res_buf, res_full, out_cnt, res_issue, res_wait, &tempty[acc]);
+      } else {
+        epilogue_tile_tma<BN, false, false>(p, &tm_out, &tm_res, t_row, mb, nb, quad, half, lane,
+                                            out_buf, res_buf, res_full, out_cnt, res_issue, res_wait,
+                                            &tempty[acc]);
       }
     }
+    if (lane == 0) tma_store_wait<0>();  // all bulk stores of this warp are complete
   }
 
   tc_fence_before();
@@ -315,16 +473,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
   }
 }
 
-template <int BN>
-int launch(const dod_gemm_args& a, cudaStream_t stream) {
-  using L = SmemLayout<BN>;
+template <int BN, bool RES>
+int launch(const dod_gemm_args& a, cudaStream_t stream, bool direct) {
+  using L = SmemLayout<BN, RES>;
   static bool attr_set = false;  // benign race: idempotent attribute
   if (!attr_set) {
-    DOD_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     L::kTotal));
+    DOD_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN, RES>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     attr_set = true;
   }
-  CUtensorMap tm_a, tm_w, tm_a2, tm_w2;
+  CUtensorMap tm_a, tm_w, tm_a2, tm_w2, tm_out, tm_res;
   if (int rc = make_tmap_2d(&tm_a, a.a, 2, a.m, a.k, a.lda, BM, BK)) return rc;
   if (int rc = make_tmap_2d(&tm_w, a.w, 2, a.n, a.k, a.ldw, BN, BK)) return rc;
   if (a.a2) {
@@ -333,6 +491,20 @@ int launch(const dod_gemm_args& a, cudaStream_t stream) {
   } else {
     tm_a2 = tm_a;
     tm_w2 = tm_w;
+  }
+  const bool out_f32 = a.out_dtype == DOD_F32;
+  const int64_t n_out = a.act == DOD_ACT_SWIGLU ? a.n / 2 : a.n;
+  if (!direct) {
+    if (int rc = make_tmap_2d(&tm_out, a.out, out_f32 ? 4 : 2, a.m, n_out, a.ldo, 32,
+                              out_f32 ? 16 : 32, 64))
+      return rc;
+  } else {
+    tm_out = tm_a;
+  }
+  if (RES && !direct) {
+    if (int rc = make_tmap_2d(&tm_res, a.residual, 4, a.m, a.n, a.ldr, 32, 16, 64)) return rc;
+  } else {
+    tm_res = tm_a;
   }
   GemmParams p;
   p.M = int(a.m);
@@ -348,12 +520,21 @@ int launch(const dod_gemm_args& a, cudaStream_t stream) {
   p.out = a.out;
   p.ldo = a.ldo;
   p.act = a.act;
-  p.out_f32 = a.out_dtype == DOD_F32;
+  p.out_f32 = out_f32;
   p.patch_rows = a.patch_rows;
+  p.direct = direct;
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_kernel<BN><<<grid, kThreads, L::kTotal, stream>>>(tm_a, tm_w, tm_a2, tm_w2, p);
+  gemm_kernel<BN, RES><<<grid, kThreads, L::kTotal, stream>>>(tm_a, tm_w, tm_a2, tm_w2, tm_out, tm_res, p);
   return check_cuda(cudaGetLastError(), "gemm_kernel launch");
+}
+
+template <int BN>
+int launch_bn(const dod_gemm_args& a, cudaStream_t stream) {
+  // TMA epilogue needs: no row remap, residual only together with fp32 output
+  const bool direct = a.patch_rows > 0 || (a.residual && a.out_dtype != DOD_F32);
+  if (a.residual && !direct) return launch<BN, true>(a, stream, false);
+  return launch<BN, false>(a, stream, direct);
 }
 
 }  // namespace
@@ -397,13 +578,13 @@ extern "C" int32_t dod_gemm_bf16(const dod_gemm_args* a, dod_stream_t stream_) {
   if (a->act == DOD_ACT_SWIGLU) {
     DOD_REQUIRE(a->n % 256 == 0 && !a->scale && !a->residual && a->patch_rows == 0,
                 "dod_gemm_bf16: SWIGLU needs n %% 256 == 0 and no scale/residual");
-    rc = launch<256>(*a, stream);
+    rc = launch_bn<256>(*a, stream);
   } else if (a->n > 128) {
-    rc = launch<256>(*a, stream);
+    rc = launch_bn<256>(*a, stream);
   } else if (a->n > 64) {
-    rc = launch<128>(*a, stream);
+    rc = launch_bn<128>(*a, stream);
   } else {
-    rc = launch<64>(*a, stream);
+    rc = launch_bn<64>(*a, stream);
   }
   if (rc == 0) count_launch();
   return rc;

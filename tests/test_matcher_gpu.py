@@ -56,7 +56,7 @@ def test_config3_bit_exact_vs_scipy(compat):
         n_same_as_oracle += int(np.array_equal(want[b][0].numpy(), ri) and np.array_equal(want[b][1].numpy(), ci))
         c_ref = matcher_oracle.cost_matrix(preds["pred_logits"][0 if compat else b], preds["pred_boxes"][0 if compat else b],
                                            t["labels"], t["boxes"]).numpy()
-        assert np.abs(cost_h[b, :, :n] - c_ref).max() < 2e-5
+        assert n == 0 or np.abs(cost_h[b, :, :n] - c_ref).max() < 2e-5
     # the CPU-computed cost differs from ours by ulps; assignments still agree (ties aside)
     assert n_same_as_oracle >= 254
 
