@@ -33,6 +33,14 @@ constexpr int kSoftmaxThreads = 128;
 constexpr int kThreads = kSoftmaxThreads + 32;  // + one TMA/MMA warp
 constexpr int kSmemBytes = kTileBytes * (1 + 2 * kKVStages) + 256 + 1024;
 
+// raw MUFU.EX2 (flush-to-zero): exp2f() wraps it in a denormal-range test + two multiplies per
+// element, which doubled the issue slots of the softmax loop
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct FmhaParams {
   int seq, heads;
   int q_off, k_off, v_off;
@@ -176,16 +184,23 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
       mbar_arrive(s_free);
 
       const int valid = p.seq - j * kTile;  // keys valid in this tile (>= 1)
-      float mx = -INFINITY;
+      if (valid < kTile) {
+        // tail tile only (1370 = 10*128 + 90): keys beyond the sequence get -inf
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= valid) sraw[c][i] = 0xff800000u;
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float v = __uint_as_float(sraw[c][i]);
-          if (c * 32 + i >= valid) v = -INFINITY;
-          sraw[c][i] = __float_as_uint(v);
-          mx = fmaxf(mx, v);
+        for (int i = 0; i < 32; i += 2) {
+          mx0 = fmaxf(mx0, __uint_as_float(sraw[c][i]));
+          mx1 = fmaxf(mx1, __uint_as_float(sraw[c][i + 1]));
         }
+      const float mx = fmaxf(mx0, mx1);
       const float m_new = fmaxf(m_used, mx * p.scale_log2);
       // lazy max: keep the stale max while it is within 2^8 of the true one
       const bool bump = (m_new - m_used) > 8.0f;
@@ -194,17 +209,20 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
         alpha = exp2f(m_used - m_new);  // 0 on the first tile (m_used = -inf)
         m_used = m_new;
       }
-      float sum = 0.0f;
+      float sum0 = 0.0f, sum1 = 0.0f;
       uint32_t pk[2][32];
+      const float neg_m = -m_used;
 #pragma unroll
       for (int c = 0; c < 4; ++c)
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float e0 = exp2f(fmaf(__uint_as_float(sraw[c][i]), p.scale_log2, -m_used));
-          const float e1 = exp2f(fmaf(__uint_as_float(sraw[c][i + 1]), p.scale_log2, -m_used));
-          sum += e0 + e1;
+          const float e0 = ex2_approx(fmaf(__uint_as_float(sraw[c][i]), p.scale_log2, neg_m));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(sraw[c][i + 1]), p.scale_log2, neg_m));
+          sum0 += e0;
+          sum1 += e1;
           pk[c >> 1][((c & 1) * 32 + i) >> 1] = pack_bf16x2(e0, e1);
         }
+      const float sum = sum0 + sum1;
       l = l * alpha + sum;
 
       if (j > 0) {
