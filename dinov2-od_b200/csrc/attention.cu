@@ -41,6 +41,30 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// exp2 on the FMA pipe (Cody-Waite + degree-3 minimax, rel. error 7.5e-5 -- P is rounded to bf16
+// right after, ulp 2^-9): x = n + f with n = rint(x), f in [-0.5, 0.5]; 2^f by Horner; n is added to
+// the exponent field with one shift-add.  Two elements per packed f32x2 instruction.  The MUFU unit
+// (16 ex2/clk/SM) is the bottleneck of the softmax at head dim 64 -- 128 ex2 per row and tile against
+// 512 tensor-pipe cycles -- so a fixed fraction of every row (kPolyMask) is evaluated here instead.
+__device__ __forceinline__ float2 exp2_poly_x2(float2 x) {
+  x.x = fmaxf(x.x, -125.0f);
+  x.y = fmaxf(x.y, -125.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f);  // 1.5 * 2^23
+  const float2 t = __fadd2_rn(x, magic);
+  const float2 n = __fadd2_rn(t, make_float2(-12582912.0f, -12582912.0f));
+  const float2 f = __fadd2_rn(x, make_float2(-n.x, -n.y));
+  float2 q = __ffma2_rn(f, make_float2(5.517166722e-02f, 5.517166722e-02f),
+                        make_float2(2.426111221e-01f, 2.426111221e-01f));
+  q = __ffma2_rn(q, f, make_float2(6.932609858e-01f, 6.932609858e-01f));
+  q = __ffma2_rn(q, f, make_float2(9.999280736e-01f, 9.999280736e-01f));
+  float2 r;
+  r.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23));
+  r.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
+  return r;
+}
+// which pairs (index mod 8) of a row take the polynomial path: 3 of 8
+constexpr uint32_t kPolyMask = 0x52;
+
 struct FmhaParams {
   int seq, heads;
   int q_off, k_off, v_off;
@@ -209,19 +233,24 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
         alpha = exp2f(m_used - m_new);  // 0 on the first tile (m_used = -inf)
         m_used = m_new;
       }
-      float sum0 = 0.0f, sum1 = 0.0f;
+      float2 sum2 = make_float2(0.0f, 0.0f);
       uint32_t pk[2][32];
-      const float neg_m = -m_used;
+      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+      const float2 nm2 = make_float2(-m_used, -m_used);
 #pragma unroll
       for (int c = 0; c < 4; ++c)
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float e0 = ex2_approx(fmaf(__uint_as_float(sraw[c][i]), p.scale_log2, neg_m));
-          const float e1 = ex2_approx(fmaf(__uint_as_float(sraw[c][i + 1]), p.scale_log2, neg_m));
-          sum0 += e0;
-          sum1 += e1;
-          pk[c >> 1][((c & 1) * 32 + i) >> 1] = pack_bf16x2(e0, e1);
+          const int pi = (c * 32 + i) >> 1;  // pair index 0..63
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(sraw[c][i]), __uint_as_float(sraw[c][i + 1])),
+                                      sc2, nm2);
+          float2 e;
+          if ((kPolyMask >> (pi & 7)) & 1) e = exp2_poly_x2(x);
+          else e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+          sum2 = __fadd2_rn(sum2, e);
+          pk[c >> 1][((c & 1) * 32 + i) >> 1] = pack_bf16x2(e.x, e.y);
         }
+      const float sum0 = sum2.x, sum1 = sum2.y;
       const float sum = sum0 + sum1;
       l = l * alpha + sum;
 

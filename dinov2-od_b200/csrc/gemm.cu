@@ -72,23 +72,32 @@ struct SmemLayout {
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
-// erf(z) ~ z * P(z^2) on |z| <= 3 (clamped beyond: 1 - erf(3) = 2.2e-5); max abs error 2.7e-5 in
-// fp32 Horner form.  Used only when the result is rounded to bf16 (ulp 2^-9): 8 FMAs instead of
-// erff's ~25 instructions, which kept the fc1 epilogue above the MMA time per tile.
-__device__ __forceinline__ float gelu_erf_bf16(float x) {
-  const float z = fminf(fmaxf(x * 0.70710678118654752440f, -3.0f), 3.0f);
-  const float s = z * z;
-  float p = 4.074217297e-08f;
-  p = fmaf(p, s, -1.944825111e-06f);
-  p = fmaf(p, s, 4.106055886e-05f);
-  p = fmaf(p, s, -5.110371310e-04f);
-  p = fmaf(p, s, 4.235428557e-03f);
-  p = fmaf(p, s, -2.510286399e-02f);
-  p = fmaf(p, s, 1.110793386e-01f);
-  p = fmaf(p, s, -3.753148772e-01f);
-  p = fmaf(p, s, 1.128268426e+00f);
-  const float hx = 0.5f * x;
-  return fmaf(hx, z * p, hx);
+// GELU for bf16 outputs.  0.5 x (1 + erf(x/sqrt2)) = x * sigmoid(2a) with
+//   erf(z) ~ tanh(a),  a = z (c0 + c1 z^2 + c2 z^4 + c3 z^6)       (max |err| 5.5e-5, monotone in z)
+// so gelu(x) = x / (1 + 2^(x * P(x^2))) with the constants below (-2 log2(e)/sqrt2 folded in); max
+// abs error 8.5e-5 against the exact erf form, 25x below the bf16 rounding of the result.  Two packed
+// elements per instruction (Blackwell f32x2 FMA/MUL/ADD) and two MUFU ops per element: ~6.5 issue
+// slots per element instead of ~33 for erff, which kept the fc1 epilogue above the MMA time per tile
+// (profiles/r01_summary.md).  fp32 outputs (fp32 mode) keep erff.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float2 gelu_bf16_x2(float2 x) {
+  const float2 s = __fmul2_rn(x, x);
+  float2 q = __ffma2_rn(s, make_float2(-2.501292636e-05f, -2.501292636e-05f),
+                        make_float2(1.148975635e-03f, 1.148975635e-03f));
+  q = __ffma2_rn(q, s, make_float2(-1.067017564e-01f, -1.067017564e-01f));
+  q = __ffma2_rn(q, s, make_float2(-2.301501626e+00f, -2.301501626e+00f));
+  const float2 a = __fmul2_rn(q, x);
+  float2 d = __fadd2_rn(make_float2(ex2_approx(a.x), ex2_approx(a.y)), make_float2(1.0f, 1.0f));
+  return __fmul2_rn(x, make_float2(rcp_approx(d.x), rcp_approx(d.y)));
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
@@ -181,8 +190,17 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
         }
       }
       if (p.act == DOD_ACT_GELU_ERF) {
+        if constexpr (OUT_F32) {
 #pragma unroll
-        for (int j = 0; j < COLS; ++j) r[j] = OUT_F32 ? gelu_erf(r[j]) : gelu_erf_bf16(r[j]);
+          for (int j = 0; j < COLS; ++j) r[j] = gelu_erf(r[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < COLS; j += 2) {
+            const float2 g = gelu_bf16_x2(make_float2(r[j], r[j + 1]));
+            r[j] = g.x;
+            r[j + 1] = g.y;
+          }
+        }
       } else if (p.act == DOD_ACT_RELU) {
 #pragma unroll
         for (int j = 0; j < COLS; ++j) r[j] = fmaxf(r[j], 0.0f);
