@@ -93,7 +93,8 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elt_bytes, uint64_t row
 }
 
 int make_tmap_3d(CUtensorMap* out, const void* base, int elt_bytes, uint64_t batch, uint64_t rows,
-                 uint64_t cols, uint64_t bs, uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
+                 uint64_t cols, uint64_t bs, uint64_t ld, uint32_t box_rows, uint32_t box_cols,
+                 int swizzle_bytes) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled driver entry point unavailable");
@@ -103,9 +104,12 @@ int make_tmap_3d(CUtensorMap* out, const void* base, int elt_bytes, uint64_t bat
   cuuint64_t strides[2] = {ld * uint64_t(elt_bytes), bs * uint64_t(elt_bytes)};
   cuuint32_t box[3] = {box_cols, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
+  const CUtensorMapSwizzle sw = swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                 : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                       : CU_TENSOR_MAP_SWIZZLE_128B;
   CUresult r = fn(out, tmap_dtype(elt_bytes), 3, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(3d batch=%llu rows=%llu cols=%llu) failed: %d",
               (unsigned long long)batch, (unsigned long long)rows, (unsigned long long)cols,

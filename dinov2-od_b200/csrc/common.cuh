@@ -48,7 +48,7 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int elt_bytes,
 int make_tmap_3d(CUtensorMap* out, const void* base, int elt_bytes,
                  uint64_t batch, uint64_t rows, uint64_t cols,
                  uint64_t bs, uint64_t ld,
-                 uint32_t box_rows, uint32_t box_cols);
+                 uint32_t box_rows, uint32_t box_cols, int swizzle_bytes = 128);
 
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------
@@ -137,6 +137,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* s
 }
 __device__ __forceinline__ void tma_store_commit() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int32_t c0,
+                                             int32_t c1, int32_t c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
 }
 template <int kPending>
 __device__ __forceinline__ void tma_store_wait_read() {

@@ -43,7 +43,7 @@ constexpr int kChunkBytes = 32 * 64;  // one epilogue chunk buffer: 32 rows x 64
 
 struct GemmParams {
   int M, N, K1blocks, K2blocks;
-  int tiles_m, tiles_n;
+  int tiles_m, tiles_n, batch;
   const float* bias;
   const float* scale;
   const float* residual;
@@ -114,8 +114,8 @@ __device__ __forceinline__ uint32_t sw64(int r, int j) { return r * 64 + ((j ^ (
 // (16 fp32 or 32 bf16 = 64 bytes per row).
 template <int BN, bool RES, bool OUT_F32>
 __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUtensorMap* tm_out,
-                                                  const CUtensorMap* tm_res, uint32_t t_row, int mb,
-                                                  int nb, int quad, int half, int lane,
+                                                  const CUtensorMap* tm_res, uint32_t t_row, int bz,
+                                                  int mb, int nb, int quad, int half, int lane,
                                                   uint8_t* out_buf, uint8_t* res_buf,
                                                   uint64_t* res_full, uint32_t& out_cnt,
                                                   uint32_t& res_issue, uint32_t& res_wait,
@@ -249,7 +249,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0 && in_range && row0 < p.M) {
-      tma_store_2d(tm_out, ob, n0, row0);
+      tma_store_3d(tm_out, ob, n0, row0, bz);
       tma_store_commit();
     }
   }
@@ -394,7 +394,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int tiles_per_batch = p.tiles_m * p.tiles_n;
+  const int num_tiles = tiles_per_batch * p.batch;
   const int kblocks = p.K1blocks + p.K2blocks;
 
   if (warp == 0) {
@@ -403,15 +404,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mb = tile / p.tiles_n, nb = tile % p.tiles_n;
+        const int bz = tile / tiles_per_batch, tl = tile % tiles_per_batch;
+        const int mb = tl / p.tiles_n, nb = tl % p.tiles_n;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* sa = stage_base + s * L::kStage;
           uint8_t* sb = sa + L::kStageA;
           mbar_expect_tx(&full[s], L::kStage);
           if (kb < p.K1blocks) {
-            tma_load_2d(sa, &tm_a, &full[s], kb * BK, mb * BM);
-            tma_load_2d(sb, &tm_w, &full[s], kb * BK, nb * BN);
+            tma_load_3d(sa, &tm_a, &full[s], kb * BK, mb * BM, bz);
+            tma_load_3d(sb, &tm_w, &full[s], kb * BK, nb * BN, bz);
           } else {
             tma_load_2d(sa, &tm_a2, &full[s], (kb - p.K1blocks) * BK, mb * BM);
             tma_load_2d(sb, &tm_w2, &full[s], (kb - p.K1blocks) * BK, nb * BN);
@@ -463,7 +465,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     uint32_t out_cnt = 0, res_issue = 0, res_wait = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int mb = tile / p.tiles_n, nb = tile % p.tiles_n;
+      const int bz = tile / tiles_per_batch, tl = tile % tiles_per_batch;
+      const int mb = tl / p.tiles_n, nb = tl % p.tiles_n;
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
       mbar_wait(&tfull[acc], acc_ph);
@@ -472,10 +475,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       if (p.direct) {
         epilogue_tile_direct<BN>(p, t_row, mb, nb, quad, half, lane, &tempty[acc]);
       } else if (p.out_f32) {
-        epilogue_tile_tma<BN, RES, true>(p, &tm_out, &tm_res, t_row, mb, nb, quad, half, lane, out_buf,
+        epilogue_tile_tma<BN, RES, true>(p, &tm_out, &tm_res, t_row, bz, mb, nb, quad, half, lane, out_buf,
                                          res_buf, res_full, out_cnt, res_issue, res_wait, &tempty[acc]);
       } else {
-        epilogue_tile_tma<BN, false, false>(p, &tm_out, &tm_res, t_row, mb, nb, quad, half, lane,
+        epilogue_tile_tma<BN, false, false>(p, &tm_out, &tm_res, t_row, bz, mb, nb, quad, half, lane,
                                             out_buf, res_buf, res_full, out_cnt, res_issue, res_wait,
                                             &tempty[acc]);
       }
@@ -501,8 +504,12 @@ int launch(const dod_gemm_args& a, cudaStream_t stream, bool direct) {
     attr_set = true;
   }
   CUtensorMap tm_a, tm_w, tm_a2, tm_w2, tm_out, tm_res;
-  if (int rc = make_tmap_2d(&tm_a, a.a, 2, a.m, a.k, a.lda, BM, BK)) return rc;
-  if (int rc = make_tmap_2d(&tm_w, a.w, 2, a.n, a.k, a.ldw, BN, BK)) return rc;
+  const uint64_t nbatch = a.batch > 1 ? uint64_t(a.batch) : 1;
+  // batch stride of a single problem only has to be a valid (16-byte multiple) TMA stride
+  const uint64_t bs_a = nbatch > 1 ? uint64_t(a.batch_stride_a) : uint64_t(a.m) * a.lda;
+  const uint64_t bs_w = nbatch > 1 ? uint64_t(a.batch_stride_w) : uint64_t(a.n) * a.ldw;
+  if (int rc = make_tmap_3d(&tm_a, a.a, 2, nbatch, a.m, a.k, bs_a, a.lda, BM, BK, 128)) return rc;
+  if (int rc = make_tmap_3d(&tm_w, a.w, 2, nbatch, a.n, a.k, bs_w, a.ldw, BN, BK, 128)) return rc;
   if (a.a2) {
     if (int rc = make_tmap_2d(&tm_a2, a.a2, 2, a.m, a.k2, a.lda2, BM, BK)) return rc;
     if (int rc = make_tmap_2d(&tm_w2, a.w2, 2, a.n, a.k2, a.ldw2, BN, BK)) return rc;
@@ -513,7 +520,8 @@ int launch(const dod_gemm_args& a, cudaStream_t stream, bool direct) {
   const bool out_f32 = a.out_dtype == DOD_F32;
   const int64_t n_out = a.act == DOD_ACT_SWIGLU ? a.n / 2 : a.n;
   if (!direct) {
-    if (int rc = make_tmap_2d(&tm_out, a.out, out_f32 ? 4 : 2, a.m, n_out, a.ldo, 32,
+    const uint64_t bs_o = nbatch > 1 ? uint64_t(a.batch_stride_out) : uint64_t(a.m) * a.ldo;
+    if (int rc = make_tmap_3d(&tm_out, a.out, out_f32 ? 4 : 2, nbatch, a.m, n_out, bs_o, a.ldo, 32,
                               out_f32 ? 16 : 32, 64))
       return rc;
   } else {
@@ -531,6 +539,7 @@ int launch(const dod_gemm_args& a, cudaStream_t stream, bool direct) {
   p.K2blocks = a.a2 ? int((a.k2 + BK - 1) / BK) : 0;
   p.tiles_m = int((a.m + BM - 1) / BM);
   p.tiles_n = int((a.n + BN - 1) / BN);
+  p.batch = int(nbatch);
   p.bias = a.bias;
   p.scale = a.scale;
   p.residual = reinterpret_cast<const float*>(a.residual);
@@ -541,7 +550,7 @@ int launch(const dod_gemm_args& a, cudaStream_t stream, bool direct) {
   p.out_f32 = out_f32;
   p.patch_rows = a.patch_rows;
   p.direct = direct;
-  const int tiles = p.tiles_m * p.tiles_n;
+  const int tiles = p.tiles_m * p.tiles_n * p.batch;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   gemm_kernel<BN, RES><<<grid, kThreads, L::kTotal, stream>>>(tm_a, tm_w, tm_a2, tm_w2, tm_out, tm_res, p);
   return check_cuda(cudaGetLastError(), "gemm_kernel launch");
@@ -583,6 +592,16 @@ extern "C" int32_t dod_gemm_bf16(const dod_gemm_args* a, dod_stream_t stream_) {
                 "dod_gemm_bf16: a2/w2 must be 16-byte aligned");
   }
   DOD_REQUIRE(a->act >= DOD_ACT_NONE && a->act <= DOD_ACT_SWIGLU, "dod_gemm_bf16: bad act");
+  if (a->batch > 1) {
+    DOD_REQUIRE(!a->residual && !a->a2 && a->patch_rows == 0,
+                "dod_gemm_bf16: batched problems take no residual / second K segment / patch rows");
+    DOD_REQUIRE(a->batch_stride_a % 8 == 0 && a->batch_stride_w % 8 == 0 &&
+                    a->batch_stride_out % (a->out_dtype == DOD_F32 ? 4 : 8) == 0 &&
+                    a->batch_stride_a > 0 && a->batch_stride_w > 0 && a->batch_stride_out > 0,
+                "dod_gemm_bf16: batch strides must be positive multiples of 16 bytes");
+    DOD_REQUIRE(a->batch * ((a->m + 127) / 128) * ((a->n + 63) / 64) < (1ll << 31),
+                "dod_gemm_bf16: too many tiles");
+  }
   DOD_REQUIRE(a->out_dtype == DOD_BF16 || a->out_dtype == DOD_F32, "dod_gemm_bf16: bad out_dtype");
   const int64_t out_cols = a->act == DOD_ACT_SWIGLU ? a->n / 2 : a->n;
   DOD_REQUIRE(a->ldo >= out_cols && a->ldo % (a->out_dtype == DOD_F32 ? 4 : 8) == 0,

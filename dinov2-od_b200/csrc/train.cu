@@ -1,0 +1,518 @@
+// Backward-pass / training-only kernels of libdod (HBM- or latency-bound helpers around the
+// tcgen05 GEMM, which does every dense contraction of the backward pass as well).
+//
+//  dod_transpose_bf16    batched [R, C] -> [C, R] (operands of the M-reduction GEMMs)
+//  dod_lowrank_wgrad     out[c, j] += alpha * sum_m big[m, c] * small[m, j]   (LoRA dA / dB, r <= 64)
+//  dod_colsum            out[c] += sum_m x[m, c]                               (bias gradients)
+//  dod_layernorm_bwd     dx (+ residual-path gradient), optional dgamma / dbeta
+//  dod_eltwise           casts, LayerScale, GELU / ReLU / SwiGLU / sigmoid derivatives, dropout
+//  dod_softmax_rows(_bwd) materialised-probability attention used by the two LoRA blocks and the
+//                        decoder in training (forward saves P, backward is four batched GEMMs)
+//  dod_deform_sample_bwd gradient of the bilinear sampling (reference deformable_attention.py:100-178)
+#include "common.cuh"
+#include "../../include/dod.h"
+
+namespace dod {
+void count_launch(int n = 1);
+namespace {
+
+__device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float ldv(const void* p, int64_t i, int dt) {
+  return dt == DOD_F32 ? reinterpret_cast<const float*>(p)[i]
+                       : bf2f(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+__device__ __forceinline__ void stv(void* p, int64_t i, int dt, float v) {
+  if (dt == DOD_F32) reinterpret_cast<float*>(p)[i] = v;
+  else reinterpret_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+}
+
+// ------------------------------------------------------------------ transpose
+__global__ void __launch_bounds__(256)
+transpose_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int rows,
+                 int cols, int64_t ld_in, int64_t ld_out, int64_t bs_in, int64_t bs_out) {
+  __shared__ __nv_bfloat16 tile[64][66];
+  const int b = blockIdx.z;
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const __nv_bfloat16* ip = in + int64_t(b) * bs_in;
+  __nv_bfloat16* op = out + int64_t(b) * bs_out;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
+  for (int r = ty; r < 64; r += 4) {
+    const int rr = r0 + r, cc = c0 + tx;
+    tile[r][tx] = (rr < rows && cc < cols) ? ip[int64_t(rr) * ld_in + cc] : __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+  for (int c = ty; c < 64; c += 4) {
+    const int cc = c0 + c, rr = r0 + tx;
+    if (cc < cols && rr < rows) op[int64_t(cc) * ld_out + rr] = tile[tx][c];
+  }
+}
+
+// ------------------------------------------------------------- low-rank wgrad
+// out[c, j] (or out[j, c]) += alpha * sum_m big[m, c] * small[m, j],  j < r <= 64.
+// grid.x = column blocks of 256, grid.y = row chunks; thread = one column, r accumulators.
+template <int R>
+__global__ void __launch_bounds__(256)
+lowrank_wgrad_kernel(const __nv_bfloat16* __restrict__ big, const __nv_bfloat16* __restrict__ small,
+                     float* __restrict__ out, int64_t m, int cols, int r, int64_t ld_big,
+                     int64_t ld_small, int64_t ldo, int transposed, float alpha, int rows_per_cta) {
+  __shared__ float ssm[32][R];
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  const int64_t m0 = int64_t(blockIdx.y) * rows_per_cta;
+  const int64_t m1 = min(m, m0 + rows_per_cta);
+  float acc[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) acc[j] = 0.f;
+  for (int64_t mm = m0; mm < m1; mm += 32) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * R; i += 256) {
+      const int rr = i / R, j = i - rr * R;
+      ssm[rr][j] = (mm + rr < m1 && j < r) ? bf2f(small[(mm + rr) * ld_small + j]) : 0.f;
+    }
+    __syncthreads();
+    if (c < cols) {
+      const int nrow = (m1 - mm) < 32 ? int(m1 - mm) : 32;
+      for (int rr = 0; rr < nrow; ++rr) {
+        const float v = bf2f(big[(mm + rr) * ld_big + c]);
+#pragma unroll
+        for (int j = 0; j < R; ++j) acc[j] = fmaf(v, ssm[rr][j], acc[j]);
+      }
+    }
+  }
+  if (c < cols) {
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+      if (j < r) atomicAdd(transposed ? out + int64_t(j) * ldo + c : out + int64_t(c) * ldo + j, alpha * acc[j]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+colsum_kernel(const void* __restrict__ x, int dt, float* __restrict__ out, int64_t m, int cols,
+              int64_t ld, int rows_per_cta) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= cols) return;
+  const int64_t m0 = int64_t(blockIdx.y) * rows_per_cta;
+  const int64_t m1 = min(m, m0 + rows_per_cta);
+  float acc = 0.f;
+  for (int64_t mm = m0; mm < m1; ++mm) acc += ldv(x, mm * ld + c, dt);
+  atomicAdd(out + c, acc);
+}
+
+// --------------------------------------------------------------- LayerNorm bwd
+// y = (x - mean) * rstd * gamma + beta.  dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),
+// g = dy * gamma.  One warp per row; statistics recomputed from x (fp32).
+constexpr int kLnMaxVec = 12;
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dt, const float* __restrict__ x,
+                     const float* __restrict__ gamma, const float* __restrict__ dres,
+                     float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                     int64_t rows, int d, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int nvec = d >> 2;
+  // per-CTA partial dgamma/dbeta in shared memory would need d floats x2; rows are few when these
+  // are requested (decoder LNs), so plain atomics per row are fine there.
+  if (row >= rows) return;
+  float4 xv[kLnMaxVec], gv[kLnMaxVec];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      xv[i] = *reinterpret_cast<const float4*>(x + row * d + c * 4);
+      s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
+    } else xv[i] = make_float4(0, 0, 0, 0);
+  }
+  const float mean = warp_sum(s) / float(d);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      xv[i].x -= mean; xv[i].y -= mean; xv[i].z -= mean; xv[i].w -= mean;
+      q += (xv[i].x * xv[i].x + xv[i].y * xv[i].y) + (xv[i].z * xv[i].z + xv[i].w * xv[i].w);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / float(d) + eps);
+  float sg = 0.f, sgx = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      xv[i].x *= rstd; xv[i].y *= rstd; xv[i].z *= rstd; xv[i].w *= rstd;  // xhat
+      float4 dyv;
+      dyv.x = ldv(dy, row * d + c * 4 + 0, dy_dt);
+      dyv.y = ldv(dy, row * d + c * 4 + 1, dy_dt);
+      dyv.z = ldv(dy, row * d + c * 4 + 2, dy_dt);
+      dyv.w = ldv(dy, row * d + c * 4 + 3, dy_dt);
+      if (dgamma) {
+        atomicAdd(dgamma + c * 4 + 0, dyv.x * xv[i].x);
+        atomicAdd(dgamma + c * 4 + 1, dyv.y * xv[i].y);
+        atomicAdd(dgamma + c * 4 + 2, dyv.z * xv[i].z);
+        atomicAdd(dgamma + c * 4 + 3, dyv.w * xv[i].w);
+        atomicAdd(dbeta + c * 4 + 0, dyv.x);
+        atomicAdd(dbeta + c * 4 + 1, dyv.y);
+        atomicAdd(dbeta + c * 4 + 2, dyv.z);
+        atomicAdd(dbeta + c * 4 + 3, dyv.w);
+      }
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+      gv[i] = make_float4(dyv.x * g.x, dyv.y * g.y, dyv.z * g.z, dyv.w * g.w);
+      sg += (gv[i].x + gv[i].y) + (gv[i].z + gv[i].w);
+      sgx += (gv[i].x * xv[i].x + gv[i].y * xv[i].y) + (gv[i].z * xv[i].z + gv[i].w * xv[i].w);
+    }
+  }
+  const float mg = warp_sum(sg) / float(d), mgx = warp_sum(sgx) / float(d);
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      float4 o;
+      o.x = rstd * (gv[i].x - mg - xv[i].x * mgx);
+      o.y = rstd * (gv[i].y - mg - xv[i].y * mgx);
+      o.z = rstd * (gv[i].z - mg - xv[i].z * mgx);
+      o.w = rstd * (gv[i].w - mg - xv[i].w * mgx);
+      if (dres) {
+        const float4 r = *reinterpret_cast<const float4*>(dres + row * d + c * 4);
+        o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+      }
+      *reinterpret_cast<float4*>(dx + row * d + c * 4) = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ elementwise
+__device__ __forceinline__ float gelu_f(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.3989422804014327f * expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+__device__ __forceinline__ uint32_t hash32(uint64_t v) {  // splitmix-style counter hash
+  v += 0x9E3779B97F4A7C15ull;
+  v = (v ^ (v >> 30)) * 0xBF58476D1CE4E5B9ull;
+  v = (v ^ (v >> 27)) * 0x94D049BB133111EBull;
+  return uint32_t((v ^ (v >> 31)) >> 32);
+}
+
+__global__ void __launch_bounds__(256)
+eltwise_kernel(int mode, const void* __restrict__ a, int a_dt, const void* __restrict__ b, int b_dt,
+               const float* __restrict__ vec, void* __restrict__ out, int out_dt, void* __restrict__ out2,
+               int out2_dt, int64_t rows, int cols, int64_t ld_a, int64_t ld_b, int64_t ld_out,
+               float p0, uint64_t seed) {
+  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int64_t r = i / cols;
+  const int c = int(i - r * cols);
+  switch (mode) {
+    case DOD_ELT_CAST: stv(out, r * ld_out + c, out_dt, ldv(a, r * ld_a + c, a_dt)); break;
+    case DOD_ELT_SCALE_COLS:  // out = a * vec[c]
+      stv(out, r * ld_out + c, out_dt, ldv(a, r * ld_a + c, a_dt) * vec[c]);
+      break;
+    case DOD_ELT_ADD: stv(out, r * ld_out + c, out_dt, ldv(a, r * ld_a + c, a_dt) + ldv(b, r * ld_b + c, b_dt)); break;
+    case DOD_ELT_GELU_FWD: stv(out, r * ld_out + c, out_dt, gelu_f(ldv(a, r * ld_a + c, a_dt))); break;
+    case DOD_ELT_GELU_BWD:  // a = upstream grad, b = pre-activation
+      stv(out, r * ld_out + c, out_dt, ldv(a, r * ld_a + c, a_dt) * gelu_grad(ldv(b, r * ld_b + c, b_dt)));
+      break;
+    case DOD_ELT_RELU_BWD:  // a = upstream grad, b = activation output
+      stv(out, r * ld_out + c, out_dt, ldv(b, r * ld_b + c, b_dt) > 0.f ? ldv(a, r * ld_a + c, a_dt) : 0.f);
+      break;
+    case DOD_ELT_SIGMOID_BWD: {  // a = upstream grad, b = sigmoid output
+      const float y = ldv(b, r * ld_b + c, b_dt);
+      stv(out, r * ld_out + c, out_dt, ldv(a, r * ld_a + c, a_dt) * y * (1.0f - y));
+      break;
+    }
+    case DOD_ELT_SWIGLU_FWD: {  // a = [rows, 2*cols] (gate | linear), out = silu(gate) * linear
+      const float g = ldv(a, r * ld_a + c, a_dt), u = ldv(a, r * ld_a + cols + c, a_dt);
+      stv(out, r * ld_out + c, out_dt, g / (1.0f + expf(-g)) * u);
+      break;
+    }
+    case DOD_ELT_SWIGLU_BWD: {  // a = upstream [rows, cols], b = pre-activation [rows, 2*cols]; out [rows, 2*cols]
+      const float g = ldv(b, r * ld_b + c, b_dt), u = ldv(b, r * ld_b + cols + c, b_dt);
+      const float dy = ldv(a, r * ld_a + c, a_dt);
+      const float sg = 1.0f / (1.0f + expf(-g));
+      stv(out, r * ld_out + c, out_dt, dy * u * (sg * (1.0f + g * (1.0f - sg))));
+      stv(out, r * ld_out + cols + c, out_dt, dy * g * sg);
+      break;
+    }
+    case DOD_ELT_DROPOUT: {  // out = a * keep / (1 - p); the mask is a pure function of (seed, i)
+      const float keep = (hash32(seed + uint64_t(i)) >> 8) * (1.0f / 16777216.0f) >= p0 ? 1.0f / (1.0f - p0) : 0.f;
+      const float v = ldv(a, r * ld_a + c, a_dt) * keep;
+      stv(out, r * ld_out + c, out_dt, v);
+      if (out2) stv(out2, r * ld_out + c, out2_dt, v);
+      break;
+    }
+    default: break;
+  }
+}
+
+// ------------------------------------------------------------------ softmax rows
+// P[row, :n] = softmax(scale * S[row, :n]) (bf16, zero padded to ldp); optional prob dropout.
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const void* __restrict__ s, int s_dt, __nv_bfloat16* __restrict__ p, int64_t rows,
+                    int n, int64_t lds, int64_t ldp, float scale, float drop_p, uint64_t seed) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float mx = -INFINITY;
+  for (int j = lane; j < n; j += 32) mx = fmaxf(mx, ldv(s, row * lds + j, s_dt) * scale);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < n; j += 32) sum += expf(ldv(s, row * lds + j, s_dt) * scale - mx);
+  const float inv = 1.0f / warp_sum(sum);
+  for (int j = lane; j < ldp; j += 32) {
+    float v = 0.f;
+    if (j < n) {
+      v = expf(ldv(s, row * lds + j, s_dt) * scale - mx) * inv;
+      if (drop_p > 0.f)
+        v = (hash32(seed + uint64_t(row) * uint64_t(ldp) + j) >> 8) * (1.0f / 16777216.0f) >= drop_p
+                ? v / (1.0f - drop_p) : 0.f;
+    }
+    p[row * ldp + j] = __float2bfloat16_rn(v);
+  }
+}
+
+// dS = scale * P * (dP - sum_k P dP)   (P = probabilities BEFORE dropout when drop_p == 0)
+__global__ void __launch_bounds__(256)
+softmax_bwd_rows_kernel(const __nv_bfloat16* __restrict__ p, const void* __restrict__ dp, int dp_dt,
+                        __nv_bfloat16* __restrict__ ds, int64_t rows, int n, int64_t ldp, int64_t lddp,
+                        int64_t ldds, float scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float dot = 0.f;
+  for (int j = lane; j < n; j += 32) dot += bf2f(p[row * ldp + j]) * ldv(dp, row * lddp + j, dp_dt);
+  dot = warp_sum(dot);
+  for (int j = lane; j < ldds; j += 32) {
+    float v = 0.f;
+    if (j < n) v = scale * bf2f(p[row * ldp + j]) * (ldv(dp, row * lddp + j, dp_dt) - dot);
+    ds[row * ldds + j] = __float2bfloat16_rn(v);
+  }
+}
+
+// ------------------------------------------------------- deformable sampling bwd
+// Gradients of dod_deform_sample w.r.t. value (atomicAdd, fp32), offsets, logits and the raw
+// reference-point logits.  One CTA per (image, query); thread = channel; per-(head, point)
+// reductions over the head's channels go through shared-memory atomics.
+__global__ void deform_sample_bwd_kernel(const void* __restrict__ value, int v_dt,
+                                         const float* __restrict__ ref, const float* __restrict__ offs,
+                                         const float* __restrict__ logits, const void* __restrict__ dout,
+                                         int do_dt, float* __restrict__ dvalue, float* __restrict__ dq,
+                                         int queries, int heads, int points, int dh, int gh, int gw,
+                                         int64_t ldv_, int64_t ldref, int64_t ldoffs, int64_t ldlog,
+                                         int64_t lddo, int64_t lddv, int64_t lddq, int ref_is_logit) {
+  extern __shared__ float sh[];  // [heads*points] dA (grad wrt attention weight), [heads*points*2] dloc
+  const int hp = heads * points;
+  float* s_dw = sh;
+  float* s_dl = sh + hp;
+  for (int i = threadIdx.x; i < 3 * hp; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int64_t row = blockIdx.x;
+  const int b = int(row / queries);
+  const int d_model = heads * dh;
+  const int64_t hw = int64_t(gh) * gw;
+  float rx = ref[row * ldref + 0], ry = ref[row * ldref + 1];
+  if (ref_is_logit) {
+    rx = 1.0f / (1.0f + expf(-rx));
+    ry = 1.0f / (1.0f + expf(-ry));
+  }
+  for (int c = threadIdx.x; c < d_model; c += blockDim.x) {
+    const int h = c / dh;
+    const float* lg = logits + row * ldlog + h * points;
+    const float* of = offs + row * ldoffs + h * points * 2;
+    float mx = -INFINITY;
+    for (int p = 0; p < points; ++p) mx = fmaxf(mx, lg[p]);
+    float den = 0.f;
+    for (int p = 0; p < points; ++p) den += expf(lg[p] - mx);
+    const float g = ldv(dout, row * lddo + c, do_dt);
+    for (int p = 0; p < points; ++p) {
+      const float wgt = expf(lg[p] - mx) / den;
+      const float ux = rx + of[2 * p + 0], uy = ry + of[2 * p + 1];
+      const float lx = fminf(fmaxf(ux, 0.f), 1.f), ly = fminf(fmaxf(uy, 0.f), 1.f);
+      const float sx = lx * float(gw - 1), sy = ly * float(gh - 1);
+      int x0 = int(floorf(sx)), y0 = int(floorf(sy));
+      int x1 = x0 + 1, y1 = y0 + 1;
+      x0 = min(max(x0, 0), gw - 1); x1 = min(max(x1, 0), gw - 1);
+      y0 = min(max(y0, 0), gh - 1); y1 = min(max(y1, 0), gh - 1);
+      const float wx1 = sx - float(x0), wx0 = 1.0f - wx1;
+      const float wy1 = sy - float(y0), wy0 = 1.0f - wy1;
+      const int64_t i00 = int64_t(y0) * gw + x0, i01 = int64_t(y1) * gw + x0;
+      const int64_t i10 = int64_t(y0) * gw + x1, i11 = int64_t(y1) * gw + x1;
+      const int64_t vb = int64_t(b) * hw;
+      const float v00 = ldv(value, (vb + i00) * ldv_ + c, v_dt), v01 = ldv(value, (vb + i01) * ldv_ + c, v_dt);
+      const float v10 = ldv(value, (vb + i10) * ldv_ + c, v_dt), v11 = ldv(value, (vb + i11) * ldv_ + c, v_dt);
+      const float samp = v00 * (wx0 * wy0) + v01 * (wx0 * wy1) + v10 * (wx1 * wy0) + v11 * (wx1 * wy1);
+      // d value
+      const float gw_ = g * wgt;
+      atomicAdd(dvalue + (vb + i00) * lddv + c, gw_ * wx0 * wy0);
+      atomicAdd(dvalue + (vb + i01) * lddv + c, gw_ * wx0 * wy1);
+      atomicAdd(dvalue + (vb + i10) * lddv + c, gw_ * wx1 * wy0);
+      atomicAdd(dvalue + (vb + i11) * lddv + c, gw_ * wx1 * wy1);
+      // d attention weight (pre-softmax handled below)
+      atomicAdd(&s_dw[h * points + p], g * samp);
+      // d location: samp depends on sx through wx1 (wx0 = 1 - wx1); the integer corners are
+      // piecewise constant.  d samp / d sx = (v10 - v00) wy0 + (v11 - v01) wy1, likewise for sy.
+      const float dsx = (v10 - v00) * wy0 + (v11 - v01) * wy1;
+      const float dsy = (v01 - v00) * wx0 + (v11 - v10) * wx1;
+      // clamp(., 0, 1) passes the gradient only strictly inside (torch.clamp: inclusive bounds pass)
+      const float px = (ux >= 0.f && ux <= 1.f) ? float(gw - 1) : 0.f;
+      const float py = (uy >= 0.f && uy <= 1.f) ? float(gh - 1) : 0.f;
+      atomicAdd(&s_dl[(h * points + p) * 2 + 0], gw_ * dsx * px);
+      atomicAdd(&s_dl[(h * points + p) * 2 + 1], gw_ * dsy * py);
+    }
+  }
+  __syncthreads();
+  // softmax backward over points, offsets and reference point
+  for (int h = threadIdx.x; h < heads; h += blockDim.x) {
+    const float* lg = logits + row * ldlog + h * points;
+    float mx = -INFINITY;
+    for (int p = 0; p < points; ++p) mx = fmaxf(mx, lg[p]);
+    float den = 0.f;
+    for (int p = 0; p < points; ++p) den += expf(lg[p] - mx);
+    float dot = 0.f;
+    for (int p = 0; p < points; ++p) dot += expf(lg[p] - mx) / den * s_dw[h * points + p];
+    for (int p = 0; p < points; ++p) {
+      const float w = expf(lg[p] - mx) / den;
+      // dq row layout = the fused query projection: [offsets 2hp | logits hp | ref 2]
+      dq[row * lddq + 2 * hp + h * points + p] = w * (s_dw[h * points + p] - dot);
+      dq[row * lddq + (h * points + p) * 2 + 0] = s_dl[(h * points + p) * 2 + 0];
+      dq[row * lddq + (h * points + p) * 2 + 1] = s_dl[(h * points + p) * 2 + 1];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float acc = 0.f;
+    for (int i = 0; i < hp; ++i) acc += s_dl[i * 2 + threadIdx.x];
+    const float r = threadIdx.x == 0 ? rx : ry;
+    dq[row * lddq + 3 * hp + threadIdx.x] = ref_is_logit ? acc * r * (1.0f - r) : acc;
+  }
+}
+
+}  // namespace
+}  // namespace dod
+
+using namespace dod;
+
+extern "C" int32_t dod_transpose_bf16(const dod_transpose_args* a, dod_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DOD_REQUIRE(a && a->in && a->out, "dod_transpose_bf16: null pointer");
+  DOD_REQUIRE(a->rows > 0 && a->cols > 0 && a->batch > 0 && a->batch <= 65535 && a->ld_in >= a->cols &&
+                  a->ld_out >= a->rows,
+              "dod_transpose_bf16: bad shape");
+  dim3 grid(unsigned((a->cols + 63) / 64), unsigned((a->rows + 63) / 64), unsigned(a->batch));
+  DOD_REQUIRE(grid.y <= 65535, "dod_transpose_bf16: too many rows");
+  transpose_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)a->in, (__nv_bfloat16*)a->out,
+                                            int(a->rows), int(a->cols), a->ld_in, a->ld_out,
+                                            a->batch_stride_in, a->batch_stride_out);
+  int rc = check_cuda(cudaGetLastError(), "transpose_kernel launch");
+  if (rc == 0) count_launch();
+  return rc;
+}
+
+extern "C" int32_t dod_lowrank_wgrad(const dod_lowrank_wgrad_args* a, dod_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DOD_REQUIRE(a && a->big && a->small && a->out, "dod_lowrank_wgrad: null pointer");
+  DOD_REQUIRE(a->m > 0 && a->cols > 0 && a->r > 0 && a->r <= 64, "dod_lowrank_wgrad: need 0 < r <= 64");
+  const int rows_per_cta = 512;
+  dim3 grid(unsigned((a->cols + 255) / 256), unsigned((a->m + rows_per_cta - 1) / rows_per_cta));
+  DOD_REQUIRE(grid.y <= 65535, "dod_lowrank_wgrad: too many rows");
+#define DOD_LRW(R)                                                                                   \
+  lowrank_wgrad_kernel<R><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)a->big,                   \
+                                                    (const __nv_bfloat16*)a->small, a->out, a->m,   \
+                                                    int(a->cols), int(a->r), a->ld_big, a->ld_small, \
+                                                    a->ldo, a->transposed, a->alpha, rows_per_cta)
+  if (a->r <= 8) DOD_LRW(8);
+  else if (a->r <= 16) DOD_LRW(16);
+  else if (a->r <= 32) DOD_LRW(32);
+  else DOD_LRW(64);
+#undef DOD_LRW
+  int rc = check_cuda(cudaGetLastError(), "lowrank_wgrad_kernel launch");
+  if (rc == 0) count_launch();
+  return rc;
+}
+
+extern "C" int32_t dod_colsum(const dod_colsum_args* a, dod_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DOD_REQUIRE(a && a->x && a->out, "dod_colsum: null pointer");
+  DOD_REQUIRE(a->m > 0 && a->cols > 0 && a->ld >= a->cols, "dod_colsum: bad shape");
+  const int rows_per_cta = 256;
+  dim3 grid(unsigned((a->cols + 255) / 256), unsigned((a->m + rows_per_cta - 1) / rows_per_cta));
+  DOD_REQUIRE(grid.y <= 65535, "dod_colsum: too many rows");
+  colsum_kernel<<<grid, 256, 0, stream>>>(a->x, a->x_dtype, a->out, a->m, int(a->cols), a->ld, rows_per_cta);
+  int rc = check_cuda(cudaGetLastError(), "colsum_kernel launch");
+  if (rc == 0) count_launch();
+  return rc;
+}
+
+extern "C" int32_t dod_layernorm_bwd(const dod_layernorm_bwd_args* a, dod_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DOD_REQUIRE(a && a->dy && a->x && a->gamma && a->dx, "dod_layernorm_bwd: null pointer");
+  DOD_REQUIRE(a->rows > 0 && a->d > 0 && a->d % 4 == 0 && a->d <= kLnMaxVec * 128,
+              "dod_layernorm_bwd: d must be a multiple of 4 and <= %d", kLnMaxVec * 128);
+  DOD_REQUIRE((a->dgamma == nullptr) == (a->dbeta == nullptr), "dod_layernorm_bwd: dgamma/dbeta go together");
+  layernorm_bwd_kernel<<<unsigned((a->rows + 7) / 8), 256, 0, stream>>>(
+      a->dy, a->dy_dtype, a->x, a->gamma, a->dres, a->dx, a->dgamma, a->dbeta, a->rows, int(a->d), a->eps);
+  int rc = check_cuda(cudaGetLastError(), "layernorm_bwd_kernel launch");
+  if (rc == 0) count_launch();
+  return rc;
+}
+
+extern "C" int32_t dod_eltwise(const dod_eltwise_args* a, dod_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DOD_REQUIRE(a && a->a && a->out, "dod_eltwise: null pointer");
+  DOD_REQUIRE(a->mode >= DOD_ELT_CAST && a->mode <= DOD_ELT_DROPOUT, "dod_eltwise: bad mode");
+  DOD_REQUIRE(a->rows >= 0 && a->cols > 0, "dod_eltwise: bad shape");
+  if (a->rows == 0) return DOD_OK;
+  const int64_t total = a->rows * a->cols;
+  eltwise_kernel<<<unsigned((total + 255) / 256), 256, 0, stream>>>(
+      a->mode, a->a, a->a_dtype, a->b, a->b_dtype, a->vec, a->out, a->out_dtype, a->out2, a->out2_dtype,
+      a->rows, int(a->cols), a->ld_a, a->ld_b, a->ld_out, a->p0, uint64_t(a->seed));
+  int rc = check_cuda(cudaGetLastError(), "eltwise_kernel launch");
+  if (rc == 0) count_launch();
+  return rc;
+}
+
+extern "C" int32_t dod_softmax_rows(const dod_softmax_rows_args* a, dod_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DOD_REQUIRE(a && a->s && a->p, "dod_softmax_rows: null pointer");
+  DOD_REQUIRE(a->rows > 0 && a->n > 0 && a->lds >= a->n && a->ldp >= a->n, "dod_softmax_rows: bad shape");
+  softmax_rows_kernel<<<unsigned((a->rows + 7) / 8), 256, 0, stream>>>(
+      a->s, a->s_dtype, (__nv_bfloat16*)a->p, a->rows, int(a->n), a->lds, a->ldp, a->scale, a->drop_p,
+      uint64_t(a->seed));
+  int rc = check_cuda(cudaGetLastError(), "softmax_rows_kernel launch");
+  if (rc == 0) count_launch();
+  return rc;
+}
+
+extern "C" int32_t dod_softmax_bwd_rows(const dod_softmax_bwd_rows_args* a, dod_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DOD_REQUIRE(a && a->p && a->dp && a->ds, "dod_softmax_bwd_rows: null pointer");
+  DOD_REQUIRE(a->rows > 0 && a->n > 0 && a->ldp >= a->n && a->lddp >= a->n && a->ldds >= a->n,
+              "dod_softmax_bwd_rows: bad shape");
+  softmax_bwd_rows_kernel<<<unsigned((a->rows + 7) / 8), 256, 0, stream>>>(
+      (const __nv_bfloat16*)a->p, a->dp, a->dp_dtype, (__nv_bfloat16*)a->ds, a->rows, int(a->n), a->ldp,
+      a->lddp, a->ldds, a->scale);
+  int rc = check_cuda(cudaGetLastError(), "softmax_bwd_rows_kernel launch");
+  if (rc == 0) count_launch();
+  return rc;
+}
+
+extern "C" int32_t dod_deform_sample_bwd(const dod_deform_sample_bwd_args* a, dod_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DOD_REQUIRE(a && a->value && a->ref && a->offs && a->logits && a->dout && a->dvalue && a->dqproj,
+              "dod_deform_sample_bwd: null pointer");
+  DOD_REQUIRE(a->batch > 0 && a->queries > 0 && a->heads > 0 && a->points > 0 && a->head_dim > 0 &&
+                  a->grid_h > 0 && a->grid_w > 0,
+              "dod_deform_sample_bwd: bad shape");
+  const int hp = int(a->heads * a->points);
+  DOD_REQUIRE(a->lddq >= 3 * hp + 2, "dod_deform_sample_bwd: dqproj rows must hold 3*H*P + 2 columns");
+  const int d_model = int(a->heads * a->head_dim);
+  const int threads = d_model >= 1024 ? 1024 : ((d_model + 31) / 32) * 32;
+  deform_sample_bwd_kernel<<<unsigned(a->batch * a->queries), threads, 3 * hp * sizeof(float), stream>>>(
+      a->value, a->value_dtype, a->ref, a->offs, a->logits, a->dout, a->dout_dtype, a->dvalue, a->dqproj,
+      int(a->queries), int(a->heads), int(a->points), int(a->head_dim), int(a->grid_h), int(a->grid_w),
+      a->ldv, a->ldref, a->ldoffs, a->ldlog, a->lddo, a->lddv, a->lddq, a->ref_is_logit);
+  int rc = check_cuda(cudaGetLastError(), "deform_sample_bwd_kernel launch");
+  if (rc == 0) count_launch();
+  return rc;
+}

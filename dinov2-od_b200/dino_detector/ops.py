@@ -251,3 +251,121 @@ def lsap(cost, tgt_offsets, max_t):
     _dod.call("dod_lsap_jv", _stream(cost), cost=cost, tgt_offsets=tgt_offsets, out_q=out_q,
               out_t=out_t, status=status, batch=b, queries=q, max_t=ld if max_t > 0 else 0, max_k=k)
     return out_q, out_t, status
+
+
+# ---------------------------------------------------------------- backward / training helpers
+ELT_CAST, ELT_SCALE_COLS, ELT_ADD, ELT_GELU_FWD, ELT_GELU_BWD, ELT_RELU_BWD, ELT_SIGMOID_BWD, \
+    ELT_SWIGLU_FWD, ELT_SWIGLU_BWD, ELT_DROPOUT = range(10)
+
+
+def gemm_batched(a, w, out, *, bias=None, act=ACT_NONE):
+    """out[b] = act(a[b] @ w[b].T + bias): a [B, M, K], w [B, N, K], out [B, M, N]; 3-D views with
+    unit inner stride and row / batch strides that are multiples of 8 elements."""
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    assert a.dim() == 3 and w.dim() == 3 and out.dim() == 3
+    assert a.stride(2) == 1 and w.stride(2) == 1 and out.stride(2) == 1
+    nb, m, k = a.shape
+    n = w.shape[1]
+    assert w.shape[0] == nb and w.shape[2] == k and tuple(out.shape) == (nb, m, n), (a.shape, w.shape, out.shape)
+    with _Timed("gemm", 2.0 * nb * m * n * k):
+        _dod.call("dod_gemm_bf16", _stream(a), a=a, w=w, m=m, n=n, k=k, lda=a.stride(1), ldw=w.stride(1),
+                  bias=bias, act=act, out=out, ldo=out.stride(1), out_dtype=_DT[out.dtype], batch=nb,
+                  batch_stride_a=a.stride(0) if nb > 1 else 0, batch_stride_w=w.stride(0) if nb > 1 else 0,
+                  batch_stride_out=out.stride(0) if nb > 1 else 0)
+    return out
+
+
+def transpose(x, out=None):
+    """bf16 [.., R, C] -> [.., C, R] (2-D or batched 3-D views with unit inner stride); the result's
+    row stride is padded to a multiple of 8 so it can feed the GEMM."""
+    assert x.dtype == torch.bfloat16 and x.stride(-1) == 1
+    x3 = x.unsqueeze(0) if x.dim() == 2 else x
+    nb, r, c = x3.shape
+    if out is None:
+        out = torch.empty((nb, c, (r + 7) // 8 * 8), dtype=torch.bfloat16, device=x.device)[:, :, :r]
+    o3 = out if out.dim() == 3 else out.unsqueeze(0)
+    _dod.call("dod_transpose_bf16", _stream(x), **{"in": x3, "out": o3, "rows": r, "cols": c,
+                                                 "ld_in": x3.stride(1), "ld_out": o3.stride(1), "batch": nb,
+                                                 "batch_stride_in": x3.stride(0),
+                                                 "batch_stride_out": o3.stride(0)})
+    return o3 if x.dim() == 3 else o3[0]
+
+
+def lowrank_wgrad(big, small, r, out, *, transposed, alpha=1.0):
+    """out[c, j] += alpha * sum_m big[m, c] * small[m, j], j < r; transposed: out[j, c]."""
+    assert big.dtype == torch.bfloat16 and small.dtype == torch.bfloat16 and out.dtype == torch.float32
+    m, cols = big.shape
+    assert small.shape[0] == m and small.shape[1] >= r
+    _dod.call("dod_lowrank_wgrad", _stream(big), big=big, small=small, out=out, m=m, cols=cols, r=r,
+              ld_big=_rowmajor(big, "big"), ld_small=_rowmajor(small, "small"), ldo=_rowmajor(out, "out"),
+              transposed=int(transposed), alpha=alpha)
+    return out
+
+
+def colsum(x, out):
+    """out[c] += sum_m x[m, c] (f32 accumulate)."""
+    m, cols = x.shape
+    assert out.dtype == torch.float32 and out.numel() >= cols
+    _dod.call("dod_colsum", _stream(x), x=x, x_dtype=_DT[x.dtype], out=out, m=m, cols=cols, ld=_rowmajor(x, "x"))
+    return out
+
+
+def layernorm_bwd(dy, x, gamma, eps, *, dres=None, dgamma=None, dbeta=None):
+    """dx (f32) of y = LN(x) given dy; dres (f32) is added; dgamma/dbeta accumulated if given."""
+    rows, d = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous() and dy.is_contiguous() and dy.shape == x.shape
+    dx = torch.empty_like(x)
+    if dres is not None:
+        assert dres.dtype == torch.float32 and dres.is_contiguous()
+    _dod.call("dod_layernorm_bwd", _stream(x), dy=dy, dy_dtype=_DT[dy.dtype], x=x, gamma=gamma, dres=dres,
+              dx=dx, dgamma=dgamma, dbeta=dbeta, rows=rows, d=d, eps=eps)
+    return dx
+
+
+def eltwise(mode, a, b=None, *, vec=None, out_dtype=None, out=None, cols=None, p0=0.0, seed=0,
+            out2_dtype=None):
+    """Elementwise helper (see dod_eltwise_mode); a, b 2-D with unit inner stride."""
+    rows = a.shape[0]
+    cols = cols if cols is not None else a.shape[1]
+    out_cols = 2 * cols if mode == ELT_SWIGLU_BWD else cols
+    if out is None:
+        out = torch.empty((rows, out_cols), dtype=out_dtype or a.dtype, device=a.device)
+    out2 = None
+    if out2_dtype is not None:
+        out2 = torch.empty((rows, out_cols), dtype=out2_dtype, device=a.device)
+    _dod.call("dod_eltwise", _stream(a), mode=mode, a=a, a_dtype=_DT[a.dtype], b=b,
+              b_dtype=_DT[b.dtype] if b is not None else 0, vec=vec, out=out, out_dtype=_DT[out.dtype],
+              out2=out2, out2_dtype=_DT[out2.dtype] if out2 is not None else 0, rows=rows, cols=cols,
+              ld_a=_rowmajor(a, "a"), ld_b=_rowmajor(b, "b") if b is not None else 0,
+              ld_out=_rowmajor(out, "out"), p0=p0, seed=seed)
+    return (out, out2) if out2 is not None else out
+
+
+def softmax_rows(s, n, scale, *, ldp=None, drop_p=0.0, seed=0):
+    """P = softmax(scale * S[:, :n]) -> bf16 [rows, ldp] (zero padded)."""
+    rows = s.shape[0]
+    ldp = ldp or (n + 7) // 8 * 8
+    p = torch.empty((rows, ldp), dtype=torch.bfloat16, device=s.device)
+    _dod.call("dod_softmax_rows", _stream(s), s=s, s_dtype=_DT[s.dtype], p=p, rows=rows, n=n,
+              lds=_rowmajor(s, "s"), ldp=ldp, scale=scale, drop_p=drop_p, seed=seed)
+    return p
+
+
+def softmax_bwd_rows(p, dp, n, scale):
+    rows = p.shape[0]
+    ds = torch.empty_like(p)
+    _dod.call("dod_softmax_bwd_rows", _stream(p), p=p, dp=dp, dp_dtype=_DT[dp.dtype], ds=ds, rows=rows, n=n,
+              ldp=_rowmajor(p, "p"), lddp=_rowmajor(dp, "dp"), ldds=_rowmajor(ds, "ds"), scale=scale)
+    return ds
+
+
+def deform_sample_bwd(value, ref, offs, logits, dout, dvalue, dqproj, batch, queries, heads, points, head_dim,
+                      grid_h, grid_w, *, ref_is_logit=True):
+    assert dvalue.dtype == torch.float32 and dqproj.dtype == torch.float32
+    _dod.call("dod_deform_sample_bwd", _stream(value), value=value, value_dtype=_DT[value.dtype], ref=ref,
+              offs=offs, logits=logits, dout=dout, dout_dtype=_DT[dout.dtype], dvalue=dvalue, dqproj=dqproj,
+              batch=batch, queries=queries, heads=heads, points=points, head_dim=head_dim, grid_h=grid_h,
+              grid_w=grid_w, ldv=_rowmajor(value, "value"), ldref=_rowmajor(ref, "ref"),
+              ldoffs=_rowmajor(offs, "offs"), ldlog=_rowmajor(logits, "logits"), lddo=_rowmajor(dout, "dout"),
+              lddv=_rowmajor(dvalue, "dvalue"), lddq=_rowmajor(dqproj, "dqproj"),
+              ref_is_logit=int(ref_is_logit))

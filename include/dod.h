@@ -84,6 +84,10 @@ typedef struct {
    * (m / P, m % P); it is stored at out row  m + m/P + 1  (token row, CLS
    * skipped) and the residual row is  1 + m % P  (position embedding).       */
   int32_t patch_rows;
+  /* batched problems (attention backward / training attention): batch > 1 runs `batch`
+   * independent GEMMs whose A / W / out start batch_stride_* ELEMENTS apart (multiples of 8).
+   * batch <= 1 (or 0) is the plain 2-D problem.  No residual / a2 / patch_rows when batched.  */
+  int64_t batch, batch_stride_a, batch_stride_w, batch_stride_out;
 } dod_gemm_args;
 DOD_API int32_t dod_gemm_bf16(const dod_gemm_args* a, dod_stream_t stream);
 
@@ -215,6 +219,94 @@ typedef struct {
   const float* src; void* dst; int64_t rows, cols, ld_src, ld_dst, kseg; int32_t w_side;
 } dod_split3_args;
 DOD_API int32_t dod_split3_bf16(const dod_split3_args* a, dod_stream_t stream);
+
+/* ---- backward pass / training helpers (csrc/train.cu) --------------------
+ * The reference trains through torch autograd (train.py:1101 loss.backward()); these are the
+ * hand-written counterparts used by dino_detector/_train.py.  All dense contractions of the
+ * backward pass go through dod_gemm_bf16 (dgrad with transposed weight copies, wgrad / attention
+ * backward with dod_transpose_bf16'd operands and the batch dimension).                         */
+typedef struct {
+  const void* in; void* out;             /* bf16 [batch, rows, cols] -> [batch, cols, rows]     */
+  int64_t rows, cols, ld_in, ld_out, batch, batch_stride_in, batch_stride_out;
+} dod_transpose_args;
+DOD_API int32_t dod_transpose_bf16(const dod_transpose_args* a, dod_stream_t stream);
+
+/* out[c, j] += alpha * sum_m big[m, c] * small[m, j]  (transposed: out[j, c]); r <= 64.
+ * LoRA gradients (utils.py:68-70): dB = alpha * dY^T (x A^T), dA = (alpha * dY B)^T x.          */
+typedef struct {
+  const void* big; const void* small; float* out;   /* bf16, bf16, f32 (accumulated)             */
+  int64_t m, cols, r, ld_big, ld_small, ldo;
+  int32_t transposed; float alpha;
+} dod_lowrank_wgrad_args;
+DOD_API int32_t dod_lowrank_wgrad(const dod_lowrank_wgrad_args* a, dod_stream_t stream);
+
+typedef struct {                                     /* out[c] += sum_m x[m, c] (bias gradients)  */
+  const void* x; int32_t x_dtype; float* out; int64_t m, cols, ld;
+} dod_colsum_args;
+DOD_API int32_t dod_colsum(const dod_colsum_args* a, dod_stream_t stream);
+
+/* LayerNorm backward: dx = dres + d/dx LN(x) . dy; dgamma/dbeta accumulated when non-NULL.     */
+typedef struct {
+  const void* dy; int32_t dy_dtype;      /* [rows, d] bf16 or f32                               */
+  const float* x;                        /* f32 [rows, d] input of the forward LayerNorm        */
+  const float* gamma;
+  const float* dres;                     /* optional f32 [rows, d] added to dx                  */
+  float* dx;                             /* f32 [rows, d]                                       */
+  float* dgamma; float* dbeta;           /* optional f32 [d], accumulated                       */
+  int64_t rows, d; float eps;
+} dod_layernorm_bwd_args;
+DOD_API int32_t dod_layernorm_bwd(const dod_layernorm_bwd_args* a, dod_stream_t stream);
+
+typedef enum {
+  DOD_ELT_CAST = 0,         /* out = a                                   */
+  DOD_ELT_SCALE_COLS = 1,   /* out = a * vec[c]      (LayerScale)        */
+  DOD_ELT_ADD = 2,          /* out = a + b                               */
+  DOD_ELT_GELU_FWD = 3,     /* out = gelu_erf(a)                         */
+  DOD_ELT_GELU_BWD = 4,     /* out = a * gelu'(b)    b = pre-activation  */
+  DOD_ELT_RELU_BWD = 5,     /* out = a * (b > 0)     b = relu output     */
+  DOD_ELT_SIGMOID_BWD = 6,  /* out = a * b (1 - b)   b = sigmoid output  */
+  DOD_ELT_SWIGLU_FWD = 7,   /* a [rows, 2 cols] -> silu(gate) * linear   */
+  DOD_ELT_SWIGLU_BWD = 8,   /* a grad [rows, cols], b pre-act [rows, 2 cols] -> out [rows, 2 cols] */
+  DOD_ELT_DROPOUT = 9       /* out = a * keep(seed, i) / (1 - p0)        */
+} dod_eltwise_mode;
+typedef struct {
+  int32_t mode;
+  const void* a; int32_t a_dtype;
+  const void* b; int32_t b_dtype;
+  const float* vec;
+  void* out; int32_t out_dtype;
+  void* out2; int32_t out2_dtype;        /* DROPOUT: optional second copy (other dtype)         */
+  int64_t rows, cols, ld_a, ld_b, ld_out;
+  float p0; int64_t seed;
+} dod_eltwise_args;
+DOD_API int32_t dod_eltwise(const dod_eltwise_args* a, dod_stream_t stream);
+
+/* P[row, :n] = softmax(scale * S[row, :n]) as bf16, zero padded to ldp columns.                */
+typedef struct {
+  const void* s; int32_t s_dtype; void* p;
+  int64_t rows, n, lds, ldp; float scale; float drop_p; int64_t seed;
+} dod_softmax_rows_args;
+DOD_API int32_t dod_softmax_rows(const dod_softmax_rows_args* a, dod_stream_t stream);
+/* dS = scale * P * (dP - rowsum(P * dP)) as bf16 (zero padded to ldds).                        */
+typedef struct {
+  const void* p; const void* dp; int32_t dp_dtype; void* ds;
+  int64_t rows, n, ldp, lddp, ldds; float scale;
+} dod_softmax_bwd_rows_args;
+DOD_API int32_t dod_softmax_bwd_rows(const dod_softmax_bwd_rows_args* a, dod_stream_t stream);
+
+/* Backward of dod_deform_sample.  dvalue (f32, [B*hw, lddv]) is accumulated with atomics and must
+ * be zeroed by the caller; dqproj rows use the fused query-projection layout
+ * [d offsets 2*H*P | d logits H*P | d reference logits 2].                                      */
+typedef struct {
+  const void* value; int32_t value_dtype;
+  const float* ref; const float* offs; const float* logits;
+  const void* dout; int32_t dout_dtype;
+  float* dvalue; float* dqproj;
+  int64_t batch, queries, heads, points, head_dim, grid_h, grid_w;
+  int64_t ldv, ldref, ldoffs, ldlog, lddo, lddv, lddq;
+  int32_t ref_is_logit;
+} dod_deform_sample_bwd_args;
+DOD_API int32_t dod_deform_sample_bwd(const dod_deform_sample_bwd_args* a, dod_stream_t stream);
 
 /* ---- Hungarian matcher ----------------------------------------------------
  * Cost matrix (reference matching.py:63,80-98):

@@ -1,0 +1,160 @@
+"""Kernel-level parity of the backward / training helpers (csrc/train.cu) against torch autograd
+or a plain torch restatement on the same seeded inputs."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from dino_detector import ops as _ops
+    return _ops
+
+
+def _g(seed):
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    return g
+
+
+def _randn(shape, g, scale=1.0):
+    return (torch.randn(shape, generator=g) * scale).cuda()
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-9)).item()
+
+
+def test_gemm_batched_strided_heads(ops):
+    """S[b] = Q_h[b] K_h[b]^T on head slices of a fused qkv buffer (training attention)."""
+    g = _g(0)
+    b, s, h = 3, 257, 4
+    d = h * 64
+    qkv = _randn((b * s, 3 * d), g).bfloat16()
+    q3 = qkv.view(b, s, 3 * d)
+    sp = (s + 7) // 8 * 8
+    for head in range(h):
+        out = torch.empty((b, s, sp), dtype=torch.float32, device="cuda")[:, :, :s]
+        ops.gemm_batched(q3[:, :, head * 64:(head + 1) * 64], q3[:, :, d + head * 64:d + (head + 1) * 64], out)
+        ref = q3[:, :, head * 64:(head + 1) * 64].float() @ q3[:, :, d + head * 64:d + (head + 1) * 64].float().transpose(1, 2)
+        assert _rel(out, ref) < 2e-5
+
+
+def test_transpose(ops):
+    g = _g(1)
+    x = _randn((3, 257, 100), g).bfloat16()
+    t = ops.transpose(x)
+    assert t.shape == (3, 100, 257) and t.stride(1) % 8 == 0
+    assert torch.equal(t, x.transpose(1, 2))
+    y = _randn((1000, 72), g).bfloat16()
+    assert torch.equal(ops.transpose(y), y.t())
+
+
+@pytest.mark.parametrize("r", [1, 2, 8, 24])
+def test_lowrank_wgrad_and_colsum(ops, r):
+    g = _g(r)
+    m, c = 3001, 777
+    big = _randn((m, c), g).bfloat16()
+    small = torch.zeros((m, 64), dtype=torch.bfloat16, device="cuda")
+    small[:, :r] = _randn((m, r), g).bfloat16()
+    out = torch.zeros((c, r), device="cuda")
+    ops.lowrank_wgrad(big, small, r, out, transposed=False, alpha=0.5)
+    ref = 0.5 * big.float().t() @ small[:, :r].float()
+    assert _rel(out, ref) < 1e-4
+    out_t = torch.zeros((r, c), device="cuda")
+    ops.lowrank_wgrad(big, small, r, out_t, transposed=True)
+    assert _rel(out_t, 2 * ref.t()) < 1e-4
+    cs = torch.zeros(c, device="cuda")
+    ops.colsum(big, cs)
+    assert _rel(cs, big.float().sum(0)) < 1e-4
+
+
+@pytest.mark.parametrize("d", [256, 768, 1024])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_layernorm_bwd(ops, d, dt):
+    g = _g(d)
+    rows = 333
+    x = (_randn((rows, d), g) * 2 + 0.5).requires_grad_(True)
+    gamma = _randn((d,), g).requires_grad_(True)
+    beta = _randn((d,), g).requires_grad_(True)
+    dy = _randn((rows, d), g).to(dt)
+    dres = _randn((rows, d), g)
+    y = torch.nn.functional.layer_norm(x, (d,), gamma, beta, 1e-5)
+    y.backward(dy.float())
+    dgamma, dbeta = torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
+    dx = ops.layernorm_bwd(dy, x.detach(), gamma.detach(), 1e-5, dres=dres, dgamma=dgamma, dbeta=dbeta)
+    assert _rel(dx - dres, x.grad) < 1e-4
+    assert _rel(dgamma, gamma.grad) < 1e-4 and _rel(dbeta, beta.grad) < 1e-4
+
+
+def test_eltwise_modes(ops):
+    g = _g(5)
+    rows, cols = 257, 384
+    a, b = _randn((rows, cols), g), _randn((rows, cols), g)
+    vec = _randn((cols,), g)
+    assert torch.equal(ops.eltwise(ops.ELT_CAST, a, out_dtype=torch.bfloat16), a.bfloat16())
+    assert torch.allclose(ops.eltwise(ops.ELT_SCALE_COLS, a, vec=vec, out_dtype=torch.float32), a * vec)
+    assert torch.allclose(ops.eltwise(ops.ELT_ADD, a, b, out_dtype=torch.float32), a + b)
+    z = a.clone().requires_grad_(True)
+    torch.nn.functional.gelu(z).backward(b)
+    assert torch.allclose(ops.eltwise(ops.ELT_GELU_FWD, a, out_dtype=torch.float32), torch.nn.functional.gelu(a), atol=1e-6)
+    assert torch.allclose(ops.eltwise(ops.ELT_GELU_BWD, b, a, out_dtype=torch.float32), z.grad, atol=1e-5)
+    relu = torch.relu(a)
+    assert torch.equal(ops.eltwise(ops.ELT_RELU_BWD, b, relu, out_dtype=torch.float32), b * (relu > 0))
+    sg = torch.sigmoid(a)
+    assert torch.allclose(ops.eltwise(ops.ELT_SIGMOID_BWD, b, sg, out_dtype=torch.float32), b * sg * (1 - sg), atol=1e-6)
+    # SwiGLU
+    zz = _randn((rows, 2 * cols), g).requires_grad_(True)
+    x1, x2 = zz.chunk(2, dim=-1)
+    y = torch.nn.functional.silu(x1) * x2
+    y.backward(b)
+    assert torch.allclose(ops.eltwise(ops.ELT_SWIGLU_FWD, zz.detach(), cols=cols, out_dtype=torch.float32), y.detach(), atol=1e-6)
+    assert torch.allclose(ops.eltwise(ops.ELT_SWIGLU_BWD, b, zz.detach(), cols=cols, out_dtype=torch.float32), zz.grad, atol=1e-5)
+    # dropout: deterministic in (seed, index), keeps ~1-p, scaled by 1/(1-p)
+    d1 = ops.eltwise(ops.ELT_DROPOUT, a, p0=0.25, seed=7, out_dtype=torch.float32)
+    d2 = ops.eltwise(ops.ELT_DROPOUT, a, p0=0.25, seed=7, out_dtype=torch.float32)
+    assert torch.equal(d1, d2)
+    kept = d1 != 0
+    assert abs(kept.float().mean().item() - 0.75) < 0.01
+    assert torch.allclose(d1[kept], a[kept] / 0.75)
+
+
+def test_softmax_rows_fwd_bwd(ops):
+    g = _g(6)
+    rows, n = 515, 1370
+    s = _randn((rows, n), g, 3.0)
+    p = ops.softmax_rows(s, n, 0.125)
+    assert p.shape == (rows, 1376) and (p[:, n:] == 0).all()
+    ref = torch.softmax(0.125 * s, dim=-1)
+    assert (p[:, :n].float() - ref).abs().max().item() < 2e-3
+    dp = _randn((rows, 1376), g)
+    ds = ops.softmax_bwd_rows(p, dp, n, 0.125)
+    pf = p[:, :n].float()
+    want = 0.125 * pf * (dp[:, :n] - (pf * dp[:, :n]).sum(-1, keepdim=True))
+    assert _rel(ds[:, :n], want) < 1e-2 and (ds[:, n:] == 0).all()
+
+
+@pytest.mark.parametrize("gh,gw", [(10, 137), (1, 257)])
+def test_deform_sample_bwd_matches_autograd(ops, gh, gw):
+    from test_kernels_gpu import _deform_ref
+    g = _g(gh)
+    b, q, h, p, dh = 2, 20, 4, 2, 64
+    hp = h * p
+    value = _randn((b * gh * gw, h * dh), g).requires_grad_(True)
+    raw = torch.zeros((b * q, 32), device="cuda")
+    raw[:, :3 * hp + 2] = _randn((b * q, 3 * hp + 2), g) * 0.5
+    raw.requires_grad_(True)
+    out = _deform_ref(value, raw[:, 3 * hp:3 * hp + 2].sigmoid(), raw[:, :2 * hp], raw[:, 2 * hp:3 * hp], b, q, h, p, dh, gh, gw)
+    dout = _randn(out.shape, g)
+    out.backward(dout)
+    dvalue = torch.zeros_like(value)
+    dq = torch.zeros((b * q, 32), device="cuda")
+    rd = raw.detach()
+    ops.deform_sample_bwd(value.detach(), rd[:, 3 * hp:3 * hp + 2], rd[:, :2 * hp], rd[:, 2 * hp:3 * hp], dout, dvalue, dq,
+                          b, q, h, p, dh, gh, gw, ref_is_logit=True)
+    assert _rel(dvalue, value.grad) < 1e-4
+    assert _rel(dq[:, :3 * hp + 2], raw.grad[:, :3 * hp + 2]) < 1e-3
