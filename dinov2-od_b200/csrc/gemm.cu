@@ -583,7 +583,12 @@ extern "C" int32_t dod_gemm_bf16(const dod_gemm_args* a, dod_stream_t stream_) {
   DOD_REQUIRE((uintptr_t(a->a) & 15) == 0 && (uintptr_t(a->w) & 15) == 0 &&
                   (uintptr_t(a->out) & 15) == 0,
               "dod_gemm_bf16: a/w/out must be 16-byte aligned");
-  DOD_REQUIRE(a->n % 8 == 0, "dod_gemm_bf16: n must be a multiple of 8 (got %lld)", (long long)a->n);
+  // bias / scale are read as float4 and the direct epilogue stores whole vectors: those need n % 8 == 0.
+  // The TMA-store epilogue clips at the tensor edge, so bias-free problems (attention scores) take any n.
+  DOD_REQUIRE(a->n % 8 == 0 || (!a->bias && !a->scale && a->patch_rows == 0 &&
+                                !(a->residual && a->out_dtype != DOD_F32) && a->act != DOD_ACT_SWIGLU),
+              "dod_gemm_bf16: n must be a multiple of 8 when bias/scale/patch rows are used (got %lld)",
+              (long long)a->n);
   if (a->a2 || a->w2) {
     DOD_REQUIRE(a->a2 && a->w2 && a->k2 > 0 && a->lda2 % 8 == 0 && a->ldw2 % 8 == 0 &&
                     a->lda2 >= a->k2 && a->ldw2 >= a->k2,

@@ -212,8 +212,9 @@ class BackbonePack:
         return self.pos_cache[key]
 
 
-def backbone_forward(pack: BackbonePack, pixel_values):
-    """-> memory [B*N, hidden] in the activation dtype of the mode, and (B, N)."""
+def backbone_forward(pack: BackbonePack, pixel_values, final_norm=True):
+    """-> memory [B*N, hidden] in the activation dtype of the mode, and (B, N).
+    final_norm=False returns the fp32 residual stream after pack.layers (training path)."""
     mode = pack.mode
     adt = torch.bfloat16 if mode == "bf16" else torch.float32
     if pixel_values.dim() != 4:
@@ -250,6 +251,8 @@ def backbone_forward(pack: BackbonePack, pixel_values):
         else:
             a = L["fc1"](hN, act=ACT_GELU_ERF)
             L["fc2"](a, scale=L["ls2"], residual=x, out=x)
+    if not final_norm:
+        return x, b, n
     mem = ops.layernorm(x, *pack.final_ln, 1e-6, out_dtype=adt)
     if pack.proj is not None:
         mem = pack.proj(mem)

@@ -28,11 +28,12 @@ def golden(name):
     return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
 
 
-def build_product_model(case, device="cpu", quiet=True):
+def build_product_model(case, device="cpu", quiet=True, **override):
     """Our DINOv2ObjectDetector for a synth.CASES entry with the synthetic weights loaded."""
     from dino_detector.models import DINOv2ObjectDetector
     from dino_detector.models import dinov2_backbone as bb
     kw = synth.case_ctor(case)
+    kw.update(override)
     bb._LAYER_OVERRIDE = synth.CASES[case].get("backbone_layers")
     try:
         with contextlib.redirect_stdout(io.StringIO() if quiet else sys.stdout):
