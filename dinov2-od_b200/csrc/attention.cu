@@ -16,6 +16,8 @@
 // (transformers modeling_dinov2.py:215-229); scale 1/sqrt(64), non-causal,
 // no mask, dropout 0.
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "../../include/dod.h"
 
@@ -29,9 +31,10 @@ constexpr int kTileBytes = kTile * kD * 2;  // 16 KB
 constexpr int kKVStages = 2;
 constexpr uint32_t kTmemCols = 256;
 constexpr uint32_t kColS = 0, kColP = 128, kColO = 192;
-constexpr int kSoftmaxThreads = 128;
+constexpr int kSoftmaxThreads = 256;  // two threads per query row (64 key columns each)
 constexpr int kThreads = kSoftmaxThreads + 32;  // + one TMA/MMA warp
-constexpr int kSmemBytes = kTileBytes * (1 + 2 * kKVStages) + 256 + 1024;
+constexpr int kXchgBytes = 2 * 2 * kTile * 4 + 2 * kTile * 4;  // max exchange (double buffered) + sums
+constexpr int kSmemBytes = kTileBytes * (1 + 2 * kKVStages) + 256 + kXchgBytes + 1024;
 
 // raw MUFU.EX2 (flush-to-zero): exp2f() wraps it in a denormal-range test + two multiplies per
 // element, which doubled the issue slots of the softmax loop
@@ -62,8 +65,6 @@ __device__ __forceinline__ float2 exp2_poly_x2(float2 x) {
   r.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
   return r;
 }
-// which pairs (index mod 8) of a row take the polynomial path: 3 of 8
-constexpr uint32_t kPolyMask = 0x52;
 
 struct FmhaParams {
   int seq, heads;
@@ -73,6 +74,13 @@ struct FmhaParams {
   int64_t ldo;
 };
 
+__device__ __forceinline__ void pair_sync(int quad) {
+  // the two warps that share a TMEM lane quadrant (rows quad*32 .. +31)
+  asm volatile("bar.sync %0, 64;" ::"r"(quad + 1) : "memory");
+}
+
+// kPolyMask: which pairs (index mod 8) of a row take the polynomial exp2 path
+template <uint32_t kPolyMask>
 __global__ void __launch_bounds__(kThreads, 2)
 fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -92,6 +100,8 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
   uint64_t* p_full = bars + 11;
   uint64_t* o_full = bars + 12;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  float* xmax = reinterpret_cast<float*>(bars + 32);  // [2 (tile parity)][2 (half)][128 rows]
+  float* xsum = xmax + 2 * 2 * kTile;                 // [2 (half)][128 rows]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -99,6 +109,7 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
   const int head = blockIdx.y;
   const int b = blockIdx.z;
   const int n_kv = (p.seq + kTile - 1) / kTile;
+  constexpr int kMmaWarp = kSoftmaxThreads / 32;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tm_qkv);
@@ -115,13 +126,13 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
-  if (warp == 4) tmem_alloc<kTmemCols>(tmem_slot);
+  if (warp == kMmaWarp) tmem_alloc<kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     if (lane == 0) {
       // ---------------- TMA + MMA issue (single thread) ----------------
       constexpr uint32_t idesc_s = make_idesc_bf16(kTile, kTile, false, false);  // Q.K^T
@@ -191,40 +202,43 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
       }
     }
   } else {
-    // ---------------- softmax warps: one query row per thread ----------------
-    const int row = warp * 32 + lane;  // row within the tile == TMEM lane
-    const uint32_t t_lane = tmem + (uint32_t(warp * 32) << 16);
+    // ---------------- softmax warps: two threads per query row ----------------
+    const int quad = warp & 3;   // TMEM lane quadrant
+    const int half = warp >> 2;  // key columns [half*64, +64) of every tile; O columns [half*32, +32)
+    const int row = quad * 32 + lane;  // row within the tile == TMEM lane
+    const uint32_t t_lane = tmem + (uint32_t(quad * 32) << 16);
     float m_used = -INFINITY;  // in log2 units (already scaled)
-    float l = 0.0f;
+    float l = 0.0f;            // partial row sum over this thread's columns
 
     for (int j = 0; j < n_kv; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      uint32_t sraw[4][32];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld_32x32(t_lane + kColS + c * 32, sraw[c]);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(s_free);
-
-      const int valid = p.seq - j * kTile;  // keys valid in this tile (>= 1)
-      if (valid < kTile) {
-        // tail tile only (1370 = 10*128 + 90): keys beyond the sequence get -inf
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i >= valid) sraw[c][i] = 0xff800000u;
-      }
+      const int valid = p.seq - j * kTile - half * 64;  // keys valid in this thread's 64 columns
+      // S is read twice from TMEM (row maximum, then exponentials), 32 columns at a time: TMEM
+      // reads are cheap and this keeps the softmax warps under the 96-register budget of 2 CTAs/SM.
       float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + kColS + half * 64 + c * 32, v);
+        tmem_ld_wait();
+        if (valid < 64) {
+          // tail tile only (1370 = 10*128 + 90): keys beyond the sequence get -inf
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= valid) v[i] = 0xff800000u;
+        }
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          mx0 = fmaxf(mx0, __uint_as_float(sraw[c][i]));
-          mx1 = fmaxf(mx1, __uint_as_float(sraw[c][i + 1]));
+          mx0 = fmaxf(mx0, __uint_as_float(v[i]));
+          mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
         }
-      const float mx = fmaxf(mx0, mx1);
+      }
+      // row maximum over both halves: exchange through shared memory (double buffered by parity)
+      float* xm = xmax + (j & 1) * 2 * kTile;
+      xm[half * kTile + row] = fmaxf(mx0, mx1);
+      pair_sync(quad);
+      const float mx = fmaxf(fmaxf(mx0, mx1), xm[(half ^ 1) * kTile + row]);
       const float m_new = fmaxf(m_used, mx * p.scale_log2);
       // lazy max: keep the stale max while it is within 2^8 of the true one
       const bool bump = (m_new - m_used) > 8.0f;
@@ -234,77 +248,83 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
         m_used = m_new;
       }
       float2 sum2 = make_float2(0.0f, 0.0f);
-      uint32_t pk[2][32];
+      uint32_t pk[32];
       const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
       const float2 nm2 = make_float2(-m_used, -m_used);
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + kColS + half * 64 + c * 32, v);
+        tmem_ld_wait();
+        if (c == 1) {
+          tc_fence_before();
+          mbar_arrive(s_free);  // S_j fully consumed: the next Q.K^T may overwrite it
+        }
+        if (valid < 64) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= valid) v[i] = 0xff800000u;
+        }
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const int pi = (c * 32 + i) >> 1;  // pair index 0..63
-          const float2 x = __ffma2_rn(make_float2(__uint_as_float(sraw[c][i]), __uint_as_float(sraw[c][i + 1])),
-                                      sc2, nm2);
+          const int pi = c * 16 + (i >> 1);  // pair index 0..31
+          const float2 x =
+              __ffma2_rn(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, nm2);
           float2 e;
           if ((kPolyMask >> (pi & 7)) & 1) e = exp2_poly_x2(x);
           else e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
           sum2 = __fadd2_rn(sum2, e);
-          pk[c >> 1][((c & 1) * 32 + i) >> 1] = pack_bf16x2(e.x, e.y);
+          pk[pi] = pack_bf16x2(e.x, e.y);
         }
-      const float sum0 = sum2.x, sum1 = sum2.y;
-      const float sum = sum0 + sum1;
-      l = l * alpha + sum;
+      }
+      l = l * alpha + (sum2.x + sum2.y);
 
       if (j > 0) {
         mbar_wait(o_full, (j - 1) & 1);  // P.V of the previous tile retired
         tc_fence_after();
         if (__any_sync(0xffffffffu, bump)) {
-          // rescale the running O row (rare after the first tiles)
+          // rescale this thread's half of the running O row (rare after the first tiles)
+          uint32_t o[32];
+          tmem_ld_32x32(t_lane + kColO + half * 32, o);
+          tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t o[32];
-            tmem_ld_32x32(t_lane + kColO + c * 32, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_32x32(t_lane + kColO + c * 32, o);
-          }
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_32x32(t_lane + kColO + half * 32, o);
         }
       }
-      tmem_st_32x32(t_lane + kColP, pk[0]);
-      tmem_st_32x32(t_lane + kColP + 32, pk[1]);
+      tmem_st_32x32(t_lane + kColP + half * 32, pk);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(p_full);
     }
 
     // ---- epilogue: O / l -> ctx ----
+    xsum[half * kTile + row] = l;
+    pair_sync(quad);
+    const float inv_l = 1.0f / (l + xsum[(half ^ 1) * kTile + row]);
     mbar_wait(o_full, (n_kv - 1) & 1);
     tc_fence_after();
-    const float inv_l = 1.0f / l;
     const int q_row = q_tile * kTile + row;
-    __nv_bfloat16* dst = p.ctx + (int64_t(b) * p.seq + q_row) * p.ldo + head * kD;
+    __nv_bfloat16* dst = p.ctx + (int64_t(b) * p.seq + q_row) * p.ldo + head * kD + half * 32;
+    uint32_t o[32];
+    tmem_ld_32x32(t_lane + kColO + half * 32, o);
+    tmem_ld_wait();
+    if (q_row < p.seq) {
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t o[32];
-      tmem_ld_32x32(t_lane + kColO + c * 32, o);
-      tmem_ld_wait();
-      if (q_row < p.seq) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          uint4 v;
-          v.x = pack_bf16x2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
-          v.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
-          v.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
-          v.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(dst + c * 32 + i) = v;
-        }
+      for (int i = 0; i < 32; i += 8) {
+        uint4 v;
+        v.x = pack_bf16x2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+        v.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+        v.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+        v.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+        *reinterpret_cast<uint4*>(dst + i) = v;
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem);
   }
@@ -327,11 +347,15 @@ extern "C" int32_t dod_fmha_fwd(const dod_fmha_args* a, dod_stream_t stream_) {
   DOD_REQUIRE(a->q_off + a->heads * kD <= a->ld && a->k_off + a->heads * kD <= a->ld &&
                   a->v_off + a->heads * kD <= a->ld && a->heads * kD <= a->ldo,
               "dod_fmha_fwd: head slices exceed the row");
-  static bool attr_set = false;
-  if (!attr_set) {
-    DOD_CUDA_OK(cudaFuncSetAttribute(fmha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     kSmemBytes));
-    attr_set = true;
+  // DOD_FMHA_POLY selects how many of every 8 exp2 pairs run on the FMA pipe (0, 2, 3 or 4)
+  static int poly = -1;
+  if (poly < 0) {
+    const char* e = getenv("DOD_FMHA_POLY");
+    poly = e ? atoi(e) : 0;  // measured best on B200: MUFU only (profiles/r01_summary.md)
+    DOD_CUDA_OK(cudaFuncSetAttribute(fmha_kernel<0x00>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    DOD_CUDA_OK(cudaFuncSetAttribute(fmha_kernel<0x12>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    DOD_CUDA_OK(cudaFuncSetAttribute(fmha_kernel<0x52>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    DOD_CUDA_OK(cudaFuncSetAttribute(fmha_kernel<0x5a>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   }
   CUtensorMap tm;
   if (int rc = make_tmap_3d(&tm, a->qkv, 2, a->batch, a->seq, a->ld, a->seq * a->ld, a->ld, kTile, kD))
@@ -346,7 +370,10 @@ extern "C" int32_t dod_fmha_fwd(const dod_fmha_args* a, dod_stream_t stream_) {
   p.ctx = reinterpret_cast<__nv_bfloat16*>(a->ctx);
   p.ldo = a->ldo;
   dim3 grid((a->seq + kTile - 1) / kTile, a->heads, a->batch);
-  fmha_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tm, p);
+  if (poly == 0) fmha_kernel<0x00><<<grid, kThreads, kSmemBytes, stream>>>(tm, p);
+  else if (poly == 2) fmha_kernel<0x12><<<grid, kThreads, kSmemBytes, stream>>>(tm, p);
+  else if (poly == 4) fmha_kernel<0x5a><<<grid, kThreads, kSmemBytes, stream>>>(tm, p);
+  else fmha_kernel<0x52><<<grid, kThreads, kSmemBytes, stream>>>(tm, p);
   int rc = check_cuda(cudaGetLastError(), "fmha_kernel launch");
   if (rc == 0) count_launch();
   return rc;

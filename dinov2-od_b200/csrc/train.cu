@@ -294,7 +294,7 @@ softmax_bwd_rows_kernel(const __nv_bfloat16* __restrict__ p, const void* __restr
 // Gradients of dod_deform_sample w.r.t. value (atomicAdd, fp32), offsets, logits and the raw
 // reference-point logits.  One CTA per (image, query); thread = channel; per-(head, point)
 // reductions over the head's channels go through shared-memory atomics.
-__global__ void deform_sample_bwd_kernel(const void* __restrict__ value, int v_dt,
+__global__ void __launch_bounds__(512) deform_sample_bwd_kernel(const void* __restrict__ value, int v_dt,
                                          const float* __restrict__ ref, const float* __restrict__ offs,
                                          const float* __restrict__ logits, const void* __restrict__ dout,
                                          int do_dt, float* __restrict__ dvalue, float* __restrict__ dq,
@@ -507,7 +507,7 @@ extern "C" int32_t dod_deform_sample_bwd(const dod_deform_sample_bwd_args* a, do
   const int hp = int(a->heads * a->points);
   DOD_REQUIRE(a->lddq >= 3 * hp + 2, "dod_deform_sample_bwd: dqproj rows must hold 3*H*P + 2 columns");
   const int d_model = int(a->heads * a->head_dim);
-  const int threads = d_model >= 1024 ? 1024 : ((d_model + 31) / 32) * 32;
+  const int threads = d_model >= 512 ? 512 : ((d_model + 31) / 32) * 32;
   deform_sample_bwd_kernel<<<unsigned(a->batch * a->queries), threads, 3 * hp * sizeof(float), stream>>>(
       a->value, a->value_dtype, a->ref, a->offs, a->logits, a->dout, a->dout_dtype, a->dvalue, a->dqproj,
       int(a->queries), int(a->heads), int(a->points), int(a->head_dim), int(a->grid_h), int(a->grid_w),
