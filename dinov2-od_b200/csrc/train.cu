@@ -242,6 +242,12 @@ eltwise_kernel(int mode, const void* __restrict__ a, int a_dt, const void* __res
       if (out2) stv(out2, r * ld_out + c, out2_dt, v);
       break;
     }
+    case DOD_ELT_AXPBY: {
+      float v = vec[0] * ldv(a, r * ld_a + c, a_dt);
+      if (b) v += vec[1] * ldv(b, r * ld_b + c, b_dt);
+      stv(out, r * ld_out + c, out_dt, v);
+      break;
+    }
     default: break;
   }
 }
@@ -460,7 +466,7 @@ extern "C" int32_t dod_layernorm_bwd(const dod_layernorm_bwd_args* a, dod_stream
 extern "C" int32_t dod_eltwise(const dod_eltwise_args* a, dod_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   DOD_REQUIRE(a && a->a && a->out, "dod_eltwise: null pointer");
-  DOD_REQUIRE(a->mode >= DOD_ELT_CAST && a->mode <= DOD_ELT_DROPOUT, "dod_eltwise: bad mode");
+  DOD_REQUIRE(a->mode >= DOD_ELT_CAST && a->mode <= DOD_ELT_AXPBY, "dod_eltwise: bad mode");
   DOD_REQUIRE(a->rows >= 0 && a->cols > 0, "dod_eltwise: bad shape");
   if (a->rows == 0) return DOD_OK;
   const int64_t total = a->rows * a->cols;

@@ -27,8 +27,25 @@ class HungarianMatcher(nn.Module):
         # every image's targets.  True reproduces that; False matches image b's own predictions.
         self.reference_compat = config.reference_compat
 
+    @staticmethod
+    def pack_targets(targets, device):
+        """List of target dicts (dataset.py:102-111) -> CSR tensors on `device`:
+        (labels i64 [T], boxes f32 [T, 4], offsets i32 [B+1], per-image counts, max count)."""
+        ns = [int(t["labels"].shape[0]) for t in targets]
+        offs = [0]
+        for n in ns:
+            offs.append(offs[-1] + n)
+        max_t = max(ns) if ns else 0
+        offsets = torch.tensor(offs, dtype=torch.int32).to(device, non_blocking=True)
+        labels = tboxes = None
+        if max_t > 0:
+            labels = torch.cat([t["labels"].reshape(-1) for t in targets]).to(device=device, dtype=torch.int64)
+            tboxes = torch.cat([t["boxes"].reshape(-1, 4) for t in targets]).to(device=device, dtype=torch.float32)
+            tboxes = tboxes.contiguous()
+        return labels, tboxes, offsets, ns, max_t
+
     @torch.no_grad()
-    def match_device(self, outputs, targets):
+    def match_device(self, outputs, targets, packed=None):
         """-> (out_q, out_t, status, counts, cost): device int32 [B, K] index arrays (first
         counts[b] entries valid), the per-image pair counts (python list) and the cost tensor."""
         logits = outputs["pred_logits"].detach()
@@ -37,19 +54,8 @@ class HungarianMatcher(nn.Module):
         bs, nq = logits.shape[:2]
         logits = logits.float().contiguous()
         boxes = boxes.float().contiguous()
-        ns = [int(t["labels"].shape[0]) for t in targets]
+        labels, tboxes, offsets, ns, max_t = packed if packed is not None else self.pack_targets(targets, dev)
         assert len(ns) == bs, "one target dict per image"
-        offs = [0]
-        for n in ns:
-            offs.append(offs[-1] + n)
-        max_t = max(ns) if ns else 0
-        offsets = torch.tensor(offs, dtype=torch.int32).to(dev, non_blocking=True)
-        if max_t > 0:
-            labels = torch.cat([t["labels"].reshape(-1) for t in targets]).to(device=dev, dtype=torch.int64)
-            tboxes = torch.cat([t["boxes"].reshape(-1, 4) for t in targets]).to(device=dev, dtype=torch.float32)
-            tboxes = tboxes.contiguous()
-        else:
-            labels = tboxes = None
         cost = ops.match_cost(logits, boxes, labels, tboxes, offsets, max_t,
                               w_class=float(self.cost_class), w_bbox=float(self.cost_bbox),
                               w_giou=float(self.cost_giou), alpha=float(self.focal_alpha),

@@ -245,8 +245,9 @@ def lsap(cost, tgt_offsets, max_t):
     b, q, ld = cost.shape
     assert cost.dtype == torch.float32 and cost.is_contiguous() and ld >= max_t
     k = max(min(q, max_t), 1)
-    out_q = torch.empty((b, k), dtype=torch.int32, device=cost.device)
-    out_t = torch.empty((b, k), dtype=torch.int32, device=cost.device)
+    # -1 = "no pair": images the solver rejects (status 1) leave their rows untouched
+    out_q = torch.full((b, k), -1, dtype=torch.int32, device=cost.device)
+    out_t = torch.full((b, k), -1, dtype=torch.int32, device=cost.device)
     status = torch.empty((b,), dtype=torch.int32, device=cost.device)
     _dod.call("dod_lsap_jv", _stream(cost), cost=cost, tgt_offsets=tgt_offsets, out_q=out_q,
               out_t=out_t, status=status, batch=b, queries=q, max_t=ld if max_t > 0 else 0, max_k=k)
@@ -255,7 +256,7 @@ def lsap(cost, tgt_offsets, max_t):
 
 # ---------------------------------------------------------------- backward / training helpers
 ELT_CAST, ELT_SCALE_COLS, ELT_ADD, ELT_GELU_FWD, ELT_GELU_BWD, ELT_RELU_BWD, ELT_SIGMOID_BWD, \
-    ELT_SWIGLU_FWD, ELT_SWIGLU_BWD, ELT_DROPOUT = range(10)
+    ELT_SWIGLU_FWD, ELT_SWIGLU_BWD, ELT_DROPOUT, ELT_AXPBY = range(11)
 
 
 def gemm_batched(a, w, out, *, bias=None, act=ACT_NONE):
@@ -369,3 +370,22 @@ def deform_sample_bwd(value, ref, offs, logits, dout, dvalue, dqproj, batch, que
               ldoffs=_rowmajor(offs, "offs"), ldlog=_rowmajor(logits, "logits"), lddo=_rowmajor(dout, "dout"),
               lddv=_rowmajor(dvalue, "dvalue"), lddq=_rowmajor(dqproj, "dqproj"),
               ref_is_logit=int(ref_is_logit))
+
+
+def criterion(logits, boxes, tgt_labels, tgt_boxes, tgt_offsets, out_q, out_t, num_boxes, *, alpha, gamma,
+              w_ce, w_bbox, w_giou):
+    """Fused SetCriterion forward+backward -> (losses [3], dlogits, dboxes_l1, dboxes_giou)."""
+    b, q, c = logits.shape
+    dev = logits.device
+    assert logits.dtype == torch.float32 and logits.is_contiguous() and boxes.is_contiguous()
+    losses = torch.zeros(3, dtype=torch.float32, device=dev)
+    dlogits = torch.empty_like(logits)
+    dboxes = torch.zeros_like(boxes)
+    dboxes_giou = torch.zeros_like(boxes)
+    tclass = torch.empty((b, q), dtype=torch.int32, device=dev)
+    _dod.call("dod_criterion", _stream(logits), logits=logits, boxes=boxes, tgt_labels=tgt_labels,
+              tgt_boxes=tgt_boxes, tgt_offsets=tgt_offsets, out_q=out_q, out_t=out_t, num_boxes=num_boxes,
+              tclass=tclass, losses=losses, dlogits=dlogits, dboxes=dboxes, dboxes_giou=dboxes_giou, batch=b,
+              queries=q, classes=c, max_k=out_q.shape[1], focal_alpha=alpha, focal_gamma=gamma, w_ce=w_ce,
+              w_bbox=w_bbox, w_giou=w_giou)
+    return losses, dlogits, dboxes, dboxes_giou

@@ -267,7 +267,8 @@ typedef enum {
   DOD_ELT_SIGMOID_BWD = 6,  /* out = a * b (1 - b)   b = sigmoid output  */
   DOD_ELT_SWIGLU_FWD = 7,   /* a [rows, 2 cols] -> silu(gate) * linear   */
   DOD_ELT_SWIGLU_BWD = 8,   /* a grad [rows, cols], b pre-act [rows, 2 cols] -> out [rows, 2 cols] */
-  DOD_ELT_DROPOUT = 9       /* out = a * keep(seed, i) / (1 - p0)        */
+  DOD_ELT_DROPOUT = 9,      /* out = a * keep(seed, i) / (1 - p0)        */
+  DOD_ELT_AXPBY = 10        /* out = vec[0] * a + vec[1] * b (b optional); vec = device scalars */
 } dod_eltwise_mode;
 typedef struct {
   int32_t mode;
@@ -345,6 +346,30 @@ typedef struct {
   int64_t batch, queries, max_t, max_k;
 } dod_lsap_args;
 DOD_API int32_t dod_lsap_jv(const dod_lsap_args* a, dod_stream_t stream);
+
+/* ---- fused SetCriterion forward + backward (reference losses.py:96-241) ---------------
+ * losses[0..2] = weighted loss_ce, loss_bbox, loss_giou (accumulated: zero them first);
+ * dlogits = d losses[0] / d pred_logits, dboxes = d losses[1] / d pred_boxes, dboxes_giou =
+ * d losses[2] / d pred_boxes (both box buffers must be zeroed first: unmatched queries get none).  The assignment is the
+ * device output of dod_lsap_jv; num_boxes is a device float (already all-reduced and clamped).  */
+typedef struct {
+  const float* logits;        /* f32 [B, Q, C]                                */
+  const float* boxes;         /* f32 [B, Q, 4] cxcywh                         */
+  const int64_t* tgt_labels;  /* i64 [T]                                      */
+  const float* tgt_boxes;     /* f32 [T, 4] (NULL when T == 0)                */
+  const int32_t* tgt_offsets; /* i32 [B+1]                                    */
+  const int32_t* out_q;       /* i32 [B, max_k] matched query per pair        */
+  const int32_t* out_t;       /* i32 [B, max_k] matched target per pair       */
+  const float* num_boxes;     /* f32 [1]                                      */
+  int32_t* tclass;            /* i32 [B, Q] scratch: target class per query   */
+  float* losses;              /* f32 [3]                                      */
+  float* dlogits;             /* f32 [B, Q, C]                                */
+  float* dboxes;              /* f32 [B, Q, 4]  L1 part                       */
+  float* dboxes_giou;         /* f32 [B, Q, 4]  GIoU part                     */
+  int64_t batch, queries, classes, max_k;
+  float focal_alpha, focal_gamma, w_ce, w_bbox, w_giou;
+} dod_criterion_args;
+DOD_API int32_t dod_criterion(const dod_criterion_args* a, dod_stream_t stream);
 
 #ifdef __cplusplus
 }

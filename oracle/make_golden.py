@@ -31,6 +31,7 @@ sys.path.insert(0, HERE)
 import synth  # noqa: E402
 import detector_oracle  # noqa: E402
 import matcher_oracle  # noqa: E402
+import criterion_oracle  # noqa: E402
 
 _LAYER_OVERRIDE = {"n": None}
 
@@ -53,12 +54,13 @@ def import_reference():
     Dinov2Model.from_pretrained = staticmethod(fake_from_pretrained)
     import dino_detector.models as ref_models
     import dino_detector.matching as ref_matching
-    return ref_models, ref_matching
+    import dino_detector.losses as ref_losses
+    return ref_models, ref_matching, ref_losses
 
 
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
-    ref_models, ref_matching = import_reference()
+    ref_models, ref_matching, ref_losses = import_reference()
     torch.set_grad_enabled(False)
     manifest = {}
     for name, case in synth.CASES.items():
@@ -106,6 +108,27 @@ def main():
             arrs[f"j{i}"] = b.numpy()
         np.savez_compressed(os.path.join(GOLDEN, f"matcher_{tag}.npz"), **arrs)
         manifest[f"matcher_{tag}"] = dict(batch=bs, queries=q, max_gt=max_gt, pred_seed=3, target_seed=4)
+    # ---- criterion: reference SetCriterion (losses.py:71-241) incl. autograd gradients ----
+    torch.set_grad_enabled(True)
+    for tag, (bs, q, max_gt) in {"q100": (8, 100, 30), "q25": (6, 25, 40)}.items():
+        preds = synth.make_predictions(bs, q, seed=5)
+        preds = {k: v.clone().requires_grad_(True) for k, v in preds.items()}
+        targets = synth.make_targets(bs, max_gt=max_gt, seed=6)
+        crit = ref_losses.SetCriterion(matcher, 91, {"loss_ce": 1.0, "loss_bbox": 5.0, "loss_giou": 2.0})
+        ld = crit(preds, targets)
+        sum(ld.values()).backward()
+        with torch.no_grad():
+            idx = matcher(preds, targets)
+        mine = criterion_oracle.set_criterion(preds["pred_logits"].detach(), preds["pred_boxes"].detach(), targets,
+                                              idx, num_classes=91)
+        print(f"criterion_{tag}:", {k: float(v) for k, v in ld.items()},
+              "oracle diff", max(abs(float(ld[k]) - float(mine[k])) for k in ld))
+        np.savez_compressed(os.path.join(GOLDEN, f"criterion_{tag}.npz"),
+                            loss_ce=ld["loss_ce"].detach().numpy(), loss_bbox=ld["loss_bbox"].detach().numpy(),
+                            loss_giou=ld["loss_giou"].detach().numpy(),
+                            dlogits=preds["pred_logits"].grad.numpy(), dboxes=preds["pred_boxes"].grad.numpy())
+        manifest[f"criterion_{tag}"] = dict(batch=bs, queries=q, max_gt=max_gt, pred_seed=5, target_seed=6)
+    torch.set_grad_enabled(False)
     with open(os.path.join(GOLDEN, "manifest.json"), "w") as fh:
         json.dump(manifest, fh, indent=1, sort_keys=True)
 

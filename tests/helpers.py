@@ -14,6 +14,7 @@ for p in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "dinov2-od_b200")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+import criterion_oracle  # noqa: E402
 import detector_oracle  # noqa: E402
 import matcher_oracle  # noqa: E402
 import synth  # noqa: E402
