@@ -46,6 +46,16 @@ BATCH = int(os.environ.get("DOD_BENCH_BATCH", 64))
 IMG = 518
 
 
+WORKLOAD = ("BASELINE configs[1]: DINOv2-B/14 detector (reference default ctor: LoRA r=2 on the last 2 blocks, "
+            "deformable decoder, 50 queries, 91 classes) inference at 518x518, 1370 tokens/image")
+
+
+def _config(world):
+    return {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": BATCH * world,
+            "parallelism": f"dp{world}", "weights": "random-init",
+            "l2_note": "per-step activations (>= 270 MB per tensor) exceed the 126 MB L2, no explicit flush"}
+
+
 def _peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
@@ -173,9 +183,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: DINOv2-B/14 detector (default ctor, deformable decoder, "
-                               "50 queries) forward at 518x518, CPU oracle port of the reference",
-                   "batch_per_step": n_img},
+        "config": dict(_config(max(1, args.gpus)), reference_arm=f"CPU oracle port of the reference forward, "
+                                                                 f"{n_img}-image sample per step, fp32"),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -316,12 +325,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: DINOv2-B/14 detector (reference default ctor: LoRA r=2 on the "
-                               "last 2 blocks, deformable decoder, 50 queries, 91 classes) inference at 518x518, "
-                               "1370 tokens/image",
-                   "batch_per_gpu": BATCH, "global_batch": BATCH * world, "parallelism": f"dp{world}",
-                   "weights": "random-init", "l2_note": "per-step activations (>= 270 MB per tensor) exceed the "
-                                                        "126 MB L2, no explicit flush"},
+        "config": _config(world),
         "roofline": roof, "roofline_other": extra, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps, "note": "pinned host images, double-buffered H2D on a copy "
