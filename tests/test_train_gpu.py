@@ -33,9 +33,10 @@ def _oracle_grads(sd, x, kw):
 #    pair of tokens whenever bf16 noise moves a sample across an integer grid boundary, so it is
 #    discontinuous in the activations and only direction-level agreement (cos >= 0.9) is meaningful;
 #    the sampling backward itself is checked exactly in fp32 in test_train_kernels_gpu.py.
-CASE_TOL = {"c1_small_std": (0.99, 0.15, 2), "large_proj_std": (0.99, 0.15, 2),
+# (min cosine, max relative error, tensors allowed above it, median relative error over tensors)
+CASE_TOL = {"c1_small_std": (0.99, 0.15, 2, 0.1), "large_proj_std": (0.99, 0.15, 2, 0.1),
             # giant3: three applications of the shared layer on a (1, 257) grid, the most position-sensitive case
-            "c1_small_deform": (0.90, 1.0, 0), "giant3_swiglu": (0.80, 1.0, 0)}
+            "c1_small_deform": (0.90, 1.0, 0, 0.2), "giant3_swiglu": (0.80, 1.0, 0, 0.3)}
 
 
 @pytest.mark.parametrize("case", ["c1_small_std", "c1_small_deform", "giant3_swiglu", "large_proj_std"])
@@ -51,7 +52,7 @@ def test_gradients_match_oracle_autograd(case):
     ref_sd, ref_out = _oracle_grads(sd, x, kw)
     assert (out["pred_logits"].detach().cpu() - ref_out["pred_logits"].detach()).abs().max() < 0.05 * ref_out["pred_logits"].abs().max()
     n_dec = kw["num_decoder_layers"]
-    min_cos, max_err, n_exempt = CASE_TOL[case]
+    min_cos, max_err, n_exempt, median_tol = CASE_TOL[case]
     rows = []
     for name, p in model.named_parameters():
         if not p.requires_grad:
@@ -78,7 +79,7 @@ def test_gradients_match_oracle_autograd(case):
     big_err = [r for r in rows if r[1] > max_err]
     assert len(big_err) <= n_exempt, big_err
     errs = sorted(r[1] for r in rows)
-    assert errs[len(errs) // 2] < 0.1, errs                                # median over tensors
+    assert errs[len(errs) // 2] < median_tol, errs                         # median over tensors
     assert torch.isfinite(all_got).all()
 
 
