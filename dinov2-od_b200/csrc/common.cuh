@@ -78,6 +78,25 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// arrive on a barrier given by its shared::cluster address (own CTA or, via mapa, a peer CTA)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// shared::cluster address of `p` (a shared::cta pointer of this CTA) inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -154,6 +173,19 @@ __device__ __forceinline__ void tma_store_wait() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(kPending) : "memory");
 }
 
+// CTA-pair (cta_group::2) TMA load: data lands in THIS CTA's shared memory, the transaction bytes
+// are credited to the mbarrier at cluster address `mbar_cluster_addr` (the leader CTA's barrier).
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMap* m,
+                                                uint32_t mbar_cluster_addr, int32_t c0, int32_t c1,
+                                                int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar_cluster_addr), "r"(c0),
+      "r"(c1), "r"(c2)
+      : "memory");
+}
+
 // ---- tcgen05 ----
 __device__ __forceinline__ void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -175,6 +207,40 @@ template <uint32_t kCols>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols)
                : "memory");
+}
+
+// CTA-pair variants (cta_group::2): one warp of EACH CTA allocates / frees; the leader CTA issues the
+// MMAs for both and signals barriers in both CTAs with a multicast commit.
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_slot) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_slot)),
+               "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols)
+               : "memory");
+}
+__device__ __forceinline__ void umma_ss_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (once all MMAs issued so far retire) on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"(mask)
+      : "memory");
 }
 
 // Shared-memory matrix descriptor, 128-byte swizzle (layout_type 2), version 1.

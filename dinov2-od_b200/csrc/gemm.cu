@@ -28,6 +28,8 @@
 // Replaces cuBLAS calls behind nn.Linear / Conv2d in the reference path (see
 // include/dod.h for file:line citations).
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "../../include/dod.h"
 
@@ -119,7 +121,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
                                                   uint8_t* out_buf, uint8_t* res_buf,
                                                   uint64_t* res_full, uint32_t& out_cnt,
                                                   uint32_t& res_issue, uint32_t& res_wait,
-                                                  uint64_t* tempty_bar) {
+                                                  uint32_t tempty_addr) {
   constexpr int COLS = OUT_F32 ? 16 : 32;
   const bool swiglu = p.act == DOD_ACT_SWIGLU;
   const int width = swiglu ? BN / 2 : BN;  // output columns of this tile
@@ -161,7 +163,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
       // this warp has read its share of the accumulator: hand the TMEM stage back
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar);
+      if (lane == 0) mbar_arrive_cluster(tempty_addr);
     }
     float r[COLS];
 #pragma unroll
@@ -259,7 +261,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
 template <int BN>
 __device__ __forceinline__ void epilogue_tile_direct(const GemmParams& p, uint32_t t_row, int mb,
                                                      int nb, int quad, int half, int lane,
-                                                     uint64_t* tempty_bar) {
+                                                     uint32_t tempty_addr) {
   const int m = mb * BM + quad * 32 + lane;
   const bool row_ok = m < p.M;
   int64_t out_row = m, res_row = m;
@@ -276,7 +278,7 @@ __device__ __forceinline__ void epilogue_tile_direct(const GemmParams& p, uint32
     if (c + 2 >= NCH) {
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar);
+      if (lane == 0) mbar_arrive_cluster(tempty_addr);
     }
     const int n0 = nb * BN + c * 32;
     if (!row_ok || n0 >= p.N) continue;
@@ -473,14 +475,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
       if (p.direct) {
-        epilogue_tile_direct<BN>(p, t_row, mb, nb, quad, half, lane, &tempty[acc]);
+        epilogue_tile_direct<BN>(p, t_row, mb, nb, quad, half, lane, smem_u32(&tempty[acc]));
       } else if (p.out_f32) {
         epilogue_tile_tma<BN, RES, true>(p, &tm_out, &tm_res, t_row, bz, mb, nb, quad, half, lane, out_buf,
-                                         res_buf, res_full, out_cnt, res_issue, res_wait, &tempty[acc]);
+                                         res_buf, res_full, out_cnt, res_issue, res_wait,
+                                         smem_u32(&tempty[acc]));
       } else {
         epilogue_tile_tma<BN, false, false>(p, &tm_out, &tm_res, t_row, bz, mb, nb, quad, half, lane,
                                             out_buf, res_buf, res_full, out_cnt, res_issue, res_wait,
-                                            &tempty[acc]);
+                                            smem_u32(&tempty[acc]));
       }
     }
     if (lane == 0) tma_store_wait<0>();  // all bulk stores of this warp are complete
@@ -492,6 +495,243 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256
+// tile.  Each CTA holds its own 128 rows of A and HALF of the W tile (128 of the 256 N rows), so
+// the shared-memory traffic per SM drops from (A 4 KB + B 8 KB) to (A 4 KB + B 4 KB) per 128-cycle
+// MMA and the TMA fill from 48 KB to 32 KB per k-block: at 128 x 256 per single CTA the two together
+// exceed the 128 B/clk shared-memory port (profiles/r01_summary.md: tensor pipe stuck at 64-70 %).
+//   * both CTAs' producers load with the cta_group::2 TMA form that credits the LEADER's full barrier;
+//     the leader arms it with the bytes of both CTAs and issues tcgen05.mma.cta_group::2 (M = 256);
+//   * tcgen05.commit multicasts to the empty / accumulator-full barriers of both CTAs;
+//   * each CTA's 8 epilogue warps drain their own 128 TMEM lanes exactly like the 1-CTA kernel and
+//     arrive on the leader's accumulator-empty barrier (remote mbarrier arrive for the peer).
+template <bool RES>
+struct SmemLayout2 {
+  static constexpr int kStageA = BM * BK * 2;   // this CTA's 128 rows of A
+  static constexpr int kStageB = 128 * BK * 2;  // this CTA's half of the 256 W rows
+  static constexpr int kStage = kStageA + kStageB;
+  static constexpr int kStages = RES ? 5 : 6;
+  static constexpr int kEpiBufs = RES ? 4 : 2;
+  static constexpr int kEpiBytes = kEpiWarps * kEpiBufs * kChunkBytes;
+  static constexpr int kBarBytes = 512;
+  static constexpr int kTotal = kStages * kStage + kEpiBytes + kBarBytes + 1024;
+  static_assert(kTotal <= 232448, "shared memory budget exceeded");
+};
+
+template <bool RES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
+             const __grid_constant__ CUtensorMap tm_a2, const __grid_constant__ CUtensorMap tm_w2,
+             const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_res,
+             const GemmParams p) {
+  using L = SmemLayout2<RES>;
+  constexpr int BN = 256;
+  constexpr int kStages = L::kStages;
+  constexpr uint32_t kTmemCols = 512;  // two accumulator stages of 256 columns (per CTA: 128 lanes)
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  uint8_t* epi_base = smem + kStages * L::kStage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_base + L::kEpiBytes);
+  uint64_t* full = bars;                        // [kStages]  used in the leader CTA only
+  uint64_t* empty = bars + kStages;             // [kStages]  one per CTA (multicast commit)
+  uint64_t* tfull = bars + 2 * kStages;         // [2]        one per CTA (multicast commit)
+  uint64_t* tempty = bars + 2 * kStages + 2;    // [2]        leader only, 2 x kEpiWarps arrivals
+  uint64_t* res_bars = bars + 2 * kStages + 4;  // [kEpiWarps][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bars + 2 * kEpiWarps);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tm_a);
+    prefetch_tmap(&tm_w);
+    if (p.K2blocks) {
+      prefetch_tmap(&tm_a2);
+      prefetch_tmap(&tm_w2);
+    }
+    prefetch_tmap(&tm_out);
+    if (RES) prefetch_tmap(&tm_res);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 2 * kEpiWarps);
+    }
+    for (int s = 0; s < 2 * kEpiWarps; ++s) mbar_init(&res_bars[s], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm<kTmemCols>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();  // barrier inits + TMEM allocation of both CTAs visible cluster-wide
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_batch = p.tiles_m * p.tiles_n;  // tiles_m counts 256-row pair tiles here
+  const int num_tiles = tiles_per_batch * p.batch;
+  const int kblocks = p.K1blocks + p.K2blocks;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int bz = tile / tiles_per_batch, tl = tile % tiles_per_batch;
+        const int mb = tl / p.tiles_n, nb = tl % p.tiles_n;
+        const int row_a = mb * 256 + int(rank) * 128;
+        const int row_w = nb * 256 + int(rank) * 128;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* sa = stage_base + s * L::kStage;
+          uint8_t* sb = sa + L::kStageA;
+          const uint32_t full_leader = map_to_cta(&full[s], 0);
+          if (rank == 0) mbar_expect_tx(&full[s], 2 * L::kStage);  // bytes of both CTAs
+          if (kb < p.K1blocks) {
+            tma_load_3d_2sm(sa, &tm_a, full_leader, kb * BK, row_a, bz);
+            tma_load_3d_2sm(sb, &tm_w, full_leader, kb * BK, row_w, bz);
+          } else {
+            tma_load_3d_2sm(sa, &tm_a2, full_leader, (kb - p.K1blocks) * BK, row_a, 0);
+            tma_load_3d_2sm(sb, &tm_w2, full_leader, (kb - p.K1blocks) * BK, row_w, 0);
+          }
+          if (++s == kStages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(256, BN, false, false);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_ph = (it >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + s * L::kStage);
+          const uint32_t sb = sa + L::kStageA;
+          const uint64_t da = make_sdesc_sw128(sa, 16, 1024);
+          const uint64_t db = make_sdesc_sw128(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_ss_2sm(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(&empty[s], 3);  // frees the stage in BOTH CTAs
+          if (kb == kblocks - 1) umma_commit_2sm(&tfull[acc], 3);
+          if (++s == kStages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..9 of both CTAs) =====================
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int ew = warp - 2;
+    uint8_t* out_buf = epi_base + ew * L::kEpiBufs * kChunkBytes;
+    uint8_t* res_buf = out_buf + 2 * kChunkBytes;
+    uint64_t* res_full = res_bars + 2 * ew;
+    uint32_t out_cnt = 0, res_issue = 0, res_wait = 0;
+    const uint32_t tempty_leader[2] = {map_to_cta(&tempty[0], 0), map_to_cta(&tempty[1], 0)};
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      const int bz = tile / tiles_per_batch, tl = tile % tiles_per_batch;
+      const int mb = (tl / p.tiles_n) * 2 + int(rank);  // 128-row block of THIS CTA
+      const int nb = tl % p.tiles_n;
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      mbar_wait(&tfull[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
+      if (p.out_f32) {
+        epilogue_tile_tma<BN, RES, true>(p, &tm_out, &tm_res, t_row, bz, mb, nb, quad, half, lane, out_buf,
+                                         res_buf, res_full, out_cnt, res_issue, res_wait, tempty_leader[acc]);
+      } else {
+        epilogue_tile_tma<BN, false, false>(p, &tm_out, &tm_res, t_row, bz, mb, nb, quad, half, lane,
+                                            out_buf, res_buf, res_full, out_cnt, res_issue, res_wait,
+                                            tempty_leader[acc]);
+      }
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // nobody exits (or frees TMEM) while the peer may still touch its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm<kTmemCols>(tmem_base);
+  }
+}
+
+template <bool RES>
+int launch2(const dod_gemm_args& a, cudaStream_t stream) {
+  using L = SmemLayout2<RES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DOD_CUDA_OK(cudaFuncSetAttribute(gemm2_kernel<RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    attr_set = true;
+  }
+  CUtensorMap tm_a, tm_w, tm_a2, tm_w2, tm_out, tm_res;
+  const uint64_t nbatch = a.batch > 1 ? uint64_t(a.batch) : 1;
+  const uint64_t bs_a = nbatch > 1 ? uint64_t(a.batch_stride_a) : uint64_t(a.m) * a.lda;
+  const uint64_t bs_w = nbatch > 1 ? uint64_t(a.batch_stride_w) : uint64_t(a.n) * a.ldw;
+  if (int rc = make_tmap_3d(&tm_a, a.a, 2, nbatch, a.m, a.k, bs_a, a.lda, 128, BK, 128)) return rc;
+  if (int rc = make_tmap_3d(&tm_w, a.w, 2, nbatch, a.n, a.k, bs_w, a.ldw, 128, BK, 128)) return rc;
+  if (a.a2) {
+    if (int rc = make_tmap_3d(&tm_a2, a.a2, 2, 1, a.m, a.k2, uint64_t(a.m) * a.lda2, a.lda2, 128, BK, 128)) return rc;
+    if (int rc = make_tmap_3d(&tm_w2, a.w2, 2, 1, a.n, a.k2, uint64_t(a.n) * a.ldw2, a.ldw2, 128, BK, 128)) return rc;
+  } else {
+    tm_a2 = tm_a;
+    tm_w2 = tm_w;
+  }
+  const bool out_f32 = a.out_dtype == DOD_F32;
+  const int64_t n_out = a.act == DOD_ACT_SWIGLU ? a.n / 2 : a.n;
+  const uint64_t bs_o = nbatch > 1 ? uint64_t(a.batch_stride_out) : uint64_t(a.m) * a.ldo;
+  if (int rc = make_tmap_3d(&tm_out, a.out, out_f32 ? 4 : 2, nbatch, a.m, n_out, bs_o, a.ldo, 32,
+                            out_f32 ? 16 : 32, 64))
+    return rc;
+  if (RES) {
+    if (int rc = make_tmap_2d(&tm_res, a.residual, 4, a.m, a.n, a.ldr, 32, 16, 64)) return rc;
+  } else {
+    tm_res = tm_a;
+  }
+  GemmParams p;
+  p.M = int(a.m);
+  p.N = int(a.n);
+  p.K1blocks = int((a.k + BK - 1) / BK);
+  p.K2blocks = a.a2 ? int((a.k2 + BK - 1) / BK) : 0;
+  p.tiles_m = int((a.m + 255) / 256);
+  p.tiles_n = int((a.n + 255) / 256);
+  p.batch = int(nbatch);
+  p.bias = a.bias;
+  p.scale = a.scale;
+  p.residual = reinterpret_cast<const float*>(a.residual);
+  p.ldr = a.ldr;
+  p.out = a.out;
+  p.ldo = a.ldo;
+  p.act = a.act;
+  p.out_f32 = out_f32;
+  p.patch_rows = 0;
+  p.direct = 0;
+  const int tiles = p.tiles_m * p.tiles_n * p.batch;
+  const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
+  gemm2_kernel<RES><<<2 * pairs, kThreads, L::kTotal, stream>>>(tm_a, tm_w, tm_a2, tm_w2, tm_out, tm_res, p);
+  return check_cuda(cudaGetLastError(), "gemm2_kernel launch");
 }
 
 template <int BN, bool RES>
@@ -556,10 +796,22 @@ int launch(const dod_gemm_args& a, cudaStream_t stream, bool direct) {
   return check_cuda(cudaGetLastError(), "gemm_kernel launch");
 }
 
+// DOD_GEMM_2CTA=0 disables the CTA-pair kernel (A/B measurements)
+bool use_pair_kernel() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DOD_GEMM_2CTA");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
+
 template <int BN>
 int launch_bn(const dod_gemm_args& a, cudaStream_t stream) {
   // TMA epilogue needs: no row remap, residual only together with fp32 output
   const bool direct = a.patch_rows > 0 || (a.residual && a.out_dtype != DOD_F32);
+  if (BN == 256 && !direct && a.m >= 512 && a.n >= 256 && use_pair_kernel())
+    return a.residual ? launch2<true>(a, stream) : launch2<false>(a, stream);
   if (a.residual && !direct) return launch<BN, true>(a, stream, false);
   return launch<BN, false>(a, stream, direct);
 }

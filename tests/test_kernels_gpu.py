@@ -49,9 +49,10 @@ def test_gemm_plain(ops, m, n, k):
     assert _rel(out_b, ref) < 1e-2
 
 
+@pytest.mark.parametrize("m", [300, 777, 2049])
 @pytest.mark.parametrize("act", ["gelu", "relu"])
-def test_gemm_act_scale_residual(ops, act):
-    m, n, k = 777, 384, 320
+def test_gemm_act_scale_residual(ops, act, m):
+    n, k = 384, 320
     g = _gen(11)
     a = _randn((m, k), g).bfloat16()
     w = _randn((n, k), g, 1 / math.sqrt(k)).bfloat16()
@@ -80,8 +81,9 @@ def test_gemm_second_k_segment(ops):
     assert _rel(out, ref) < 2e-5
 
 
-def test_gemm_swiglu(ops):
-    m, k, hidden = 500, 256, 512
+@pytest.mark.parametrize("m", [500, 1111])     # 1-CTA kernel / CTA-pair kernel
+def test_gemm_swiglu(ops, m):
+    k, hidden = 256, 512
     g = _gen(6)
     x = _randn((m, k), g).bfloat16()
     w_in = _randn((2 * hidden, k), g, 1 / math.sqrt(k))
