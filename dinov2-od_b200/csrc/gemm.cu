@@ -74,32 +74,29 @@ struct SmemLayout {
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
-// GELU for bf16 outputs.  0.5 x (1 + erf(x/sqrt2)) = x * sigmoid(2a) with
-//   erf(z) ~ tanh(a),  a = z (c0 + c1 z^2 + c2 z^4 + c3 z^6)       (max |err| 5.5e-5, monotone in z)
-// so gelu(x) = x / (1 + 2^(x * P(x^2))) with the constants below (-2 log2(e)/sqrt2 folded in); max
-// abs error 8.5e-5 against the exact erf form, 25x below the bf16 rounding of the result.  Two packed
-// elements per instruction (Blackwell f32x2 FMA/MUL/ADD) and two MUFU ops per element: ~6.5 issue
-// slots per element instead of ~33 for erff, which kept the fc1 epilogue above the MMA time per tile
-// (profiles/r01_summary.md).  fp32 outputs (fp32 mode) keep erff.
-__device__ __forceinline__ float ex2_approx(float x) {
+// GELU for bf16 outputs.  0.5 x (1 + erf(x/sqrt2)) with
+//   erf(z) ~ tanh(a),  a = z (c0 + c1 z^2 + c2 z^4 + c3 z^6)      (max |err| 5.5e-5, monotone in z)
+// i.e. gelu(x) = hx + hx * tanh(x * P(x^2)), hx = x/2 (constants below have 1/sqrt2 folded in).  Formula
+// error 8.5e-5 abs; tanh.approx.f32 (one MUFU op, rel. error 2^-11) adds <= 2.5e-4 |x| -- together
+// under 1/8 of the bf16 rounding of the result.  Two packed elements per instruction (Blackwell
+// f32x2 FMA/MUL) and ONE MUFU op per element: ~3.5 issue slots per element instead of ~33 for erff,
+// which kept the fc1 epilogue above the MMA time per tile (profiles/r01_summary.md; an exp2 + rcp
+// sigmoid form with two MUFU ops per element still left fc1 at 59 % tensor-pipe).  fp32 outputs
+// (fp32 mode) keep erff.
+__device__ __forceinline__ float tanh_approx(float x) {
   float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float rcp_approx(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 __device__ __forceinline__ float2 gelu_bf16_x2(float2 x) {
   const float2 s = __fmul2_rn(x, x);
-  float2 q = __ffma2_rn(s, make_float2(-2.501292636e-05f, -2.501292636e-05f),
-                        make_float2(1.148975635e-03f, 1.148975635e-03f));
-  q = __ffma2_rn(q, s, make_float2(-1.067017564e-01f, -1.067017564e-01f));
-  q = __ffma2_rn(q, s, make_float2(-2.301501626e+00f, -2.301501626e+00f));
+  float2 q = __ffma2_rn(s, make_float2(8.668819692e-06f, 8.668819692e-06f),
+                        make_float2(-3.982046110e-04f, -3.982046110e-04f));
+  q = __ffma2_rn(q, s, make_float2(3.698001081e-02f, 3.698001081e-02f));
+  q = __ffma2_rn(q, s, make_float2(7.976396815e-01f, 7.976396815e-01f));
   const float2 a = __fmul2_rn(q, x);
-  float2 d = __fadd2_rn(make_float2(ex2_approx(a.x), ex2_approx(a.y)), make_float2(1.0f, 1.0f));
-  return __fmul2_rn(x, make_float2(rcp_approx(d.x), rcp_approx(d.y)));
+  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  return __ffma2_rn(hx, make_float2(tanh_approx(a.x), tanh_approx(a.y)), hx);
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
