@@ -90,7 +90,7 @@ def lib():
             alt = {"dod_gemm_bf16": "dod_gemm_args", "dod_patchify14": "dod_patchify_args",
                    "dod_pos_resize_bicubic": "dod_pos_resize_args", "dod_fmha_fwd": "dod_fmha_args",
                    "dod_cast_pad_bf16": "dod_cast_pad_args", "dod_split3_bf16": "dod_split3_args",
-                   "dod_lsap_jv": "dod_lsap_args", "dod_transpose_bf16": "dod_transpose_args"}.get(fn, sname)
+                   "dod_lsap_jv": "dod_lsap_args", "dod_transpose_bf16": "dod_transpose_args", "dod_adam_step": "dod_adam_args"}.get(fn, sname)
             if alt in STRUCTS:
                 f = getattr(l, fn)
                 f.argtypes = [ctypes.POINTER(STRUCTS[alt]), ctypes.c_void_p]

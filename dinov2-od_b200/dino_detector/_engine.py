@@ -150,10 +150,20 @@ def pack_raw(weight, bias, mode):
     return PackedLinear(weight.detach().float(), bias.detach().float() if bias is not None else None, mode)
 
 
+_weight_epoch = 0
+
+
+def bump_weight_epoch():
+    """Called by writers that update parameters outside torch's version counters (optim.FusedAdam
+    writes through a flat buffer with its own kernel): invalidates every cached weight pack."""
+    global _weight_epoch
+    _weight_epoch += 1
+
+
 def params_version(module):
     """Cheap fingerprint of every parameter's storage + in-place version (optimizer steps,
-    load_state_dict and .to() all change it)."""
-    return tuple((p.data_ptr(), p._version) for p in module.parameters())
+    load_state_dict and .to() all change it) + the libdod weight epoch."""
+    return (_weight_epoch,) + tuple((p.data_ptr(), p._version) for p in module.parameters())
 
 
 def f32c(t):

@@ -389,3 +389,19 @@ def criterion(logits, boxes, tgt_labels, tgt_boxes, tgt_offsets, out_q, out_t, n
               queries=q, classes=c, max_k=out_q.shape[1], focal_alpha=alpha, focal_gamma=gamma, w_ce=w_ce,
               w_bbox=w_bbox, w_giou=w_giou)
     return losses, dlogits, dboxes, dboxes_giou
+
+
+def sumsq(x, out):
+    """out[0] += sum(x^2) for a flat f32 tensor."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and out.dtype == torch.float32
+    _dod.call("dod_sumsq", _stream(x), x=x, n=x.numel(), out=out)
+    return out
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, step, *, lr, beta1, beta2, eps, weight_decay,
+              grad_sumsq=None, max_grad_norm=0.0):
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == param.numel()
+    _dod.call("dod_adam_step", _stream(param), param=param, grad=grad, exp_avg=exp_avg, exp_avg_sq=exp_avg_sq,
+              n=param.numel(), step=step, grad_sumsq=grad_sumsq, max_grad_norm=max_grad_norm, lr=lr,
+              beta1=beta1, beta2=beta2, eps=eps, weight_decay=weight_decay)

@@ -1,0 +1,60 @@
+"""Fused clip + Adam on flat buffers (reference train.py:1000-1004, 1104-1110).
+
+`FusedAdam` re-homes the trainable parameters into one flat fp32 buffer (each `p.data` becomes a view),
+keeps their gradients in the `FlatGradSync` buffer that is also the NCCL all-reduce payload, and runs
+`clip_grad_norm_(params, max_norm)` + `Adam.step()` as two kernel launches for the whole model with no
+host sync.  Semantics are torch.optim.Adam's (L2 weight decay added to the gradient, bias correction,
+eps outside the square root) and torch.nn.utils.clip_grad_norm_'s (norm over the trainable gradients,
+coef = min(1, max_norm / (norm + 1e-6))).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _engine, ops
+from .parallel import FlatGradSync
+
+
+class FusedAdam:
+    def __init__(self, params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, max_grad_norm=1.0,
+                 process_group=None):
+        self.sync = FlatGradSync(params, process_group)
+        ps = self.sync.params
+        dev = ps[0].device
+        self.flat_param = torch.empty(self.sync.numel, dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p in ps:
+                n = p.numel()
+                view = self.flat_param[off:off + n].view_as(p)
+                view.copy_(p.data)
+                p.data = view                         # parameters now live in the flat buffer
+                off += n
+        self.exp_avg = torch.zeros_like(self.flat_param)
+        self.exp_avg_sq = torch.zeros_like(self.flat_param)
+        self.norm_sq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.max_grad_norm = max_grad_norm
+        self.step_count = 0
+
+    def zero_grad(self):
+        self.sync.zero()
+
+    def step(self, all_reduce=True):
+        """(all-reduce the flat gradient,) clip by global norm and apply Adam."""
+        if all_reduce:
+            self.sync.all_reduce(average=True)
+        self.step_count += 1
+        self.norm_sq.zero_()
+        if self.max_grad_norm and self.max_grad_norm > 0:
+            ops.sumsq(self.sync.flat, self.norm_sq)
+        ops.adam_step(self.flat_param, self.sync.flat, self.exp_avg, self.exp_avg_sq, self.step_count,
+                      lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
+                      weight_decay=self.weight_decay, grad_sumsq=self.norm_sq,
+                      max_grad_norm=float(self.max_grad_norm or 0.0))
+        # the update went through the flat buffer, not torch's per-tensor version counters
+        _engine.bump_weight_epoch()
+
+    def grad_norm(self):
+        """Global gradient norm of the last step (device tensor; reading it syncs)."""
+        return self.norm_sq.sqrt()

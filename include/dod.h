@@ -371,6 +371,21 @@ typedef struct {
 } dod_criterion_args;
 DOD_API int32_t dod_criterion(const dod_criterion_args* a, dod_stream_t stream);
 
+/* ---- fused clip + Adam over flat buffers (reference train.py:1000-1004, 1104-1110) -------
+ * out[0] += sum x^2;  then  coef = min(1, max_norm / (sqrt(sumsq) + 1e-6)),
+ * g = coef*g + wd*p, m = b1 m + (1-b1) g, v = b2 v + (1-b2) g^2,
+ * p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)      (torch.optim.Adam, L2 weight decay)  */
+typedef struct { const float* x; int64_t n; float* out; } dod_sumsq_args;
+DOD_API int32_t dod_sumsq(const dod_sumsq_args* a, dod_stream_t stream);
+typedef struct {
+  float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
+  int64_t n, step;               /* step >= 1                                   */
+  const float* grad_sumsq;       /* device float: sum of squared gradients      */
+  float max_grad_norm;           /* <= 0: no clipping                           */
+  float lr, beta1, beta2, eps, weight_decay;
+} dod_adam_args;
+DOD_API int32_t dod_adam_step(const dod_adam_args* a, dod_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
