@@ -405,3 +405,20 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, step, *, lr, beta1, beta2, eps, 
     _dod.call("dod_adam_step", _stream(param), param=param, grad=grad, exp_avg=exp_avg, exp_avg_sq=exp_avg_sq,
               n=param.numel(), step=step, grad_sumsq=grad_sumsq, max_grad_norm=max_grad_norm, lr=lr,
               beta1=beta1, beta2=beta2, eps=eps, weight_decay=weight_decay)
+
+
+def postprocess(logits, boxes, threshold=0.05):
+    """-> (scores [B, cap], boxes_xywh [B, cap, 4], classes [B, cap], counts [B]) on the device."""
+    b, q, c = logits.shape
+    logits = logits.float().contiguous()
+    boxes = boxes.float().contiguous()
+    cap = q * (c - 1)
+    dev = logits.device
+    out_score = torch.empty((b, cap), dtype=torch.float32, device=dev)
+    out_box = torch.empty((b, cap, 4), dtype=torch.float32, device=dev)
+    out_class = torch.empty((b, cap), dtype=torch.int32, device=dev)
+    counts = torch.empty((b,), dtype=torch.int32, device=dev)
+    _dod.call("dod_postprocess", _stream(logits), logits=logits, boxes=boxes, out_score=out_score,
+              out_box=out_box, out_class=out_class, counts=counts, batch=b, queries=q, classes=c, capacity=cap,
+              threshold=threshold)
+    return out_score, out_box, out_class, counts

@@ -84,3 +84,36 @@ def generalized_box_iou(boxes1, boxes2):
     wh_e = (rb_e - lt_e).clamp(min=0)
     area_e = wh_e[:, :, 0] * wh_e[:, :, 1]
     return iou - (area_e - union) / area_e
+
+
+def coco_detections(outputs, image_ids, threshold=0.05):
+    """Detector outputs -> list of COCO result dicts, same content and order as the loops at
+    reference utils.py:195-233 (class 0 skipped, score > threshold, bbox = [x, y, w, h])."""
+    from . import ops
+    scores, boxes, classes, counts = ops.postprocess(outputs["pred_logits"], outputs["pred_boxes"], threshold)
+    counts = counts.cpu().tolist()                      # one small D2H copy
+    results = []
+    for b, n in enumerate(counts):
+        if n == 0:
+            continue
+        s, bx, cl = scores[b, :n].cpu().tolist(), boxes[b, :n].cpu().tolist(), classes[b, :n].cpu().tolist()
+        img_id = int(image_ids[b])
+        results.extend({"image_id": img_id, "category_id": int(c), "bbox": [float(v) for v in box], "score": float(sc)}
+                       for sc, box, c in zip(s, bx, cl))
+    return results
+
+
+def evaluate_coco(model, dataloader, device, output_file=None):
+    """reference utils.py:167-240 (tqdm progress bar omitted): forward + COCO-format detections."""
+    import json
+    model.eval()
+    results = []
+    with torch.no_grad():
+        for images, targets in dataloader:
+            outputs = model(images.to(device))
+            ids = [int(t.get("image_id", i)) for i, t in enumerate(targets)]
+            results.extend(coco_detections(outputs, ids))
+    if output_file is not None:
+        with open(output_file, "w") as f:
+            json.dump(results, f)
+    return results

@@ -371,6 +371,16 @@ typedef struct {
 } dod_criterion_args;
 DOD_API int32_t dod_criterion(const dod_criterion_args* a, dod_stream_t stream);
 
+/* ---- COCO post-processing (reference utils.py:195-233) ------------------------------------
+ * Per image b: every (class c >= 1, query q) with sigmoid(logit) > threshold, in (c, q) order:
+ * out_score[b, i], out_class[b, i], out_box[b, i] = [x1, y1, x2 - x1, y2 - y1]; counts[b] entries.  */
+typedef struct {
+  const float* logits; const float* boxes;      /* f32 [B, Q, C], f32 [B, Q, 4] cxcywh            */
+  float* out_score; float* out_box; int32_t* out_class; int32_t* counts;   /* [B, cap], [B, cap, 4], [B, cap], [B] */
+  int64_t batch, queries, classes, capacity; float threshold;
+} dod_postprocess_args;
+DOD_API int32_t dod_postprocess(const dod_postprocess_args* a, dod_stream_t stream);
+
 /* ---- fused clip + Adam over flat buffers (reference train.py:1000-1004, 1104-1110) -------
  * out[0] += sum x^2;  then  coef = min(1, max_norm / (sqrt(sumsq) + 1e-6)),
  * g = coef*g + wd*p, m = b1 m + (1-b1) g, v = b2 v + (1-b2) g^2,

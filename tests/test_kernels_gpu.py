@@ -338,3 +338,18 @@ def test_lsap_ties_and_shapes(ops):
     bad[0, 3, 2] = float("nan")
     _, _, st = ops.lsap(bad.cuda(), torch.tensor([0, 4], dtype=torch.int32).cuda(), 4)
     assert st.cpu().item() == 1
+
+
+def test_add_layernorm(ops):
+    """y = LayerNorm(x + r) (decoder post-norm helper of the C ABI)."""
+    from dino_detector import _dod
+    g = _gen(77)
+    rows, d = 301, 256
+    x, r = _randn((rows, d), g), _randn((rows, d), g).bfloat16()
+    gamma, beta = _randn((d,), g), _randn((d,), g)
+    y = torch.empty((rows, d), device="cuda")
+    y16 = torch.empty((rows, d), device="cuda", dtype=torch.bfloat16)
+    _dod.call("dod_add_layernorm", torch.cuda.current_stream().cuda_stream, x=x, r=r, r_dtype=0, gamma=gamma,
+              beta=beta, y=y, y_bf16=y16, rows=rows, d=d, eps=1e-5)
+    ref = torch.nn.functional.layer_norm(x + r.float(), (d,), gamma, beta, 1e-5)
+    assert _rel(y, ref) < 1e-5 and _rel(y16, ref) < 1e-2
