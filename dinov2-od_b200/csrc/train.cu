@@ -278,20 +278,28 @@ softmax_rows_kernel(const void* __restrict__ s, int s_dt, __nv_bfloat16* __restr
   }
 }
 
-// dS = scale * P * (dP - sum_k P dP)   (P = probabilities BEFORE dropout when drop_p == 0)
+// dS = scale * P * (dP' - sum_k P dP'), P = probabilities BEFORE dropout; with attention dropout
+// dP' = dP * keep / (1 - p) where keep is the mask softmax_rows_kernel drew for (seed, row, j).
 __global__ void __launch_bounds__(256)
 softmax_bwd_rows_kernel(const __nv_bfloat16* __restrict__ p, const void* __restrict__ dp, int dp_dt,
                         __nv_bfloat16* __restrict__ ds, int64_t rows, int n, int64_t ldp, int64_t lddp,
-                        int64_t ldds, float scale) {
+                        int64_t ldds, float scale, float drop_p, uint64_t seed) {
   const int lane = threadIdx.x & 31;
   const int64_t row = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
+  const float keep_scale = drop_p > 0.f ? 1.0f / (1.0f - drop_p) : 1.0f;
+  auto dpe = [&](int j) {
+    float v = ldv(dp, row * lddp + j, dp_dt);
+    if (drop_p > 0.f)
+      v = (hash32(seed + uint64_t(row) * uint64_t(ldp) + j) >> 8) * (1.0f / 16777216.0f) >= drop_p ? v * keep_scale : 0.f;
+    return v;
+  };
   float dot = 0.f;
-  for (int j = lane; j < n; j += 32) dot += bf2f(p[row * ldp + j]) * ldv(dp, row * lddp + j, dp_dt);
+  for (int j = lane; j < n; j += 32) dot += bf2f(p[row * ldp + j]) * dpe(j);
   dot = warp_sum(dot);
   for (int j = lane; j < ldds; j += 32) {
     float v = 0.f;
-    if (j < n) v = scale * bf2f(p[row * ldp + j]) * (ldv(dp, row * lddp + j, dp_dt) - dot);
+    if (j < n) v = scale * bf2f(p[row * ldp + j]) * (dpe(j) - dot);
     ds[row * ldds + j] = __float2bfloat16_rn(v);
   }
 }
@@ -497,7 +505,7 @@ extern "C" int32_t dod_softmax_bwd_rows(const dod_softmax_bwd_rows_args* a, dod_
               "dod_softmax_bwd_rows: bad shape");
   softmax_bwd_rows_kernel<<<unsigned((a->rows + 7) / 8), 256, 0, stream>>>(
       (const __nv_bfloat16*)a->p, a->dp, a->dp_dtype, (__nv_bfloat16*)a->ds, a->rows, int(a->n), a->ldp,
-      a->lddp, a->ldds, a->scale);
+      a->lddp, a->ldds, a->scale, a->drop_p, uint64_t(a->seed));
   int rc = check_cuda(cudaGetLastError(), "softmax_bwd_rows_kernel launch");
   if (rc == 0) count_launch();
   return rc;

@@ -17,9 +17,9 @@ What runs where
     accumulates into the fp32 gradient, LoRA wgrad with dod_lowrank_wgrad (HBM-bound, r <= 64);
   * gradients w.r.t. activations travel as fp32 on the residual stream and bf16 into GEMMs.
 
-bf16 mode only (fp32 mode is an inference/parity mode).  Attention-probability dropout of
-nn.MultiheadAttention is not applied in train mode (the four residual-branch dropouts of each
-decoder layer are); DESIGN.md lists this deviation.
+bf16 mode only (fp32 mode is an inference/parity mode).  Train-mode dropout (the four residual-branch
+dropouts of each decoder layer and nn.MultiheadAttention's attention-probability dropout) uses a
+counter-hash mask that the backward regenerates; the RNG stream differs from torch's by design.
 """
 from __future__ import annotations
 
@@ -161,25 +161,45 @@ class LLinear:
 # ---------------------------------------------------------------------------
 # attention backward (materialised probabilities, batched tcgen05 GEMMs)
 # ---------------------------------------------------------------------------
-def attention_bwd(q3, k3, v3, dctx3, dq3, dk3, dv3, heads, dh, scale):
+def attention_fwd_dropout(q3, k3, v3, heads, dh, scale, drop_p, seed):
+    """Materialised attention forward with dropout on the probabilities (nn.MultiheadAttention in
+    train mode): ctx = dropout(softmax(Q K^T * scale)) V, per head with the batched GEMM."""
+    b, lq, d = q3.shape
+    lk = k3.shape[1]
+    lkp = _pad8(lk)
+    ctx = torch.empty((b, lq, d), dtype=BF16, device=q3.device)
+    for h in range(heads):
+        sl = slice(h * dh, (h + 1) * dh)
+        s_full = torch.empty((b, lq, lkp), dtype=F32, device=q3.device)
+        ops.gemm_batched(q3[:, :, sl], k3[:, :, sl], s_full[:, :, :lk])
+        pd = ops.softmax_rows(s_full.view(b * lq, lkp), lk, scale, ldp=lkp, drop_p=drop_p, seed=seed + (h << 24))
+        ops.gemm_batched(pd.view(b, lq, lkp)[:, :, :lk], ops.transpose(v3[:, :, sl]), ctx[:, :, sl])
+    return ctx
+
+
+def attention_bwd(q3, k3, v3, dctx3, dq3, dk3, dv3, heads, dh, scale, drop_p=0.0, seed=0):
     """q3 [B, Lq, H*dh], k3/v3 [B, Lk, H*dh], dctx3 [B, Lq, H*dh] (bf16 3-D views, unit inner
-    stride); writes bf16 gradients into the dq3/dk3/dv3 views."""
+    stride); writes bf16 gradients into the dq3/dk3/dv3 views.  drop_p/seed: the attention dropout
+    mask of attention_fwd_dropout is regenerated from the counter hash."""
     b, lq, _ = q3.shape
     lk = k3.shape[1]
     lkp = _pad8(lk)
     dev = q3.device
     for h in range(heads):
         sl = slice(h * dh, (h + 1) * dh)
+        hseed = seed + (h << 24)
         qh, kh, vh, doh = q3[:, :, sl], k3[:, :, sl], v3[:, :, sl], dctx3[:, :, sl]
         s_full = torch.empty((b, lq, lkp), dtype=F32, device=dev)
         ops.gemm_batched(qh, kh, s_full[:, :, :lk])                                  # S = Q K^T
         p = ops.softmax_rows(s_full.view(b * lq, lkp), lk, scale, ldp=lkp)           # P  [B*Lq, lkp]
+        pd = p if drop_p <= 0 else ops.softmax_rows(s_full.view(b * lq, lkp), lk, scale, ldp=lkp,
+                                                     drop_p=drop_p, seed=hseed)      # dropout(P)
         ops.gemm_batched(doh, vh, s_full[:, :, :lk])                                 # dP = dO V^T
-        ds = ops.softmax_bwd_rows(p, s_full.view(b * lq, lkp), lk, scale)            # dS [B*Lq, lkp]
-        ds3, p3 = ds.view(b, lq, lkp)[:, :, :lk], p.view(b, lq, lkp)[:, :, :lk]
+        ds = ops.softmax_bwd_rows(p, s_full.view(b * lq, lkp), lk, scale, drop_p=drop_p, seed=hseed)
+        ds3, pd3 = ds.view(b, lq, lkp)[:, :, :lk], pd.view(b, lq, lkp)[:, :, :lk]
         ops.gemm_batched(ds3, ops.transpose(kh), dq3[:, :, sl])                      # dQ = dS K
         ops.gemm_batched(ops.transpose(ds3), ops.transpose(qh), dk3[:, :, sl])       # dK = dS^T Q
-        ops.gemm_batched(ops.transpose(p3), ops.transpose(doh), dv3[:, :, sl])       # dV = P^T dO
+        ops.gemm_batched(ops.transpose(pd3), ops.transpose(doh), dv3[:, :, sl])      # dV = dropout(P)^T dO
 
 
 # ---------------------------------------------------------------------------
@@ -416,7 +436,12 @@ def train_forward(model, pixel_values):
         sv = {"tgt": tgt, "tgt32": tgt32}
         seed = st.seed + (li << 36)
         sv["qkv"] = L.sa_in.fwd(tgt)
-        ctx = ops.mha_small(sv["qkv"][:, :hd], sv["qkv"][:, hd:2 * hd], sv["qkv"][:, 2 * hd:], b, q, q, nh, dh, scale)
+        if p_drop > 0:
+            qkv3 = sv["qkv"].view(b, q, -1)
+            ctx = attention_fwd_dropout(qkv3[:, :, :hd], qkv3[:, :, hd:2 * hd], qkv3[:, :, 2 * hd:3 * hd], nh, dh,
+                                        scale, p_drop, seed + 5).view(b * q, hd)
+        else:
+            ctx = ops.mha_small(sv["qkv"][:, :hd], sv["qkv"][:, hd:2 * hd], sv["qkv"][:, 2 * hd:], b, q, q, nh, dh, scale)
         sv["ctx_sa"] = ctx
         sv["x1"] = _dropout_add(L.sa_out.fwd(ctx, out_dtype=F32), tgt32, p_drop, seed + 1)
         t1_32, t1 = L.n1.fwd(sv["x1"])
@@ -433,7 +458,12 @@ def train_forward(model, pixel_values):
         else:
             sv["cq"] = L.ca_q.fwd(t1)
             sv["kv"] = L.ca_kv.fwd(mem)
-            sv["ctx_ca"] = ops.mha_small(sv["cq"], sv["kv"][:, :hd], sv["kv"][:, hd:], b, q, n, nh, dh, scale)
+            if p_drop > 0:
+                kv3 = sv["kv"].view(b, n, 2 * hd)
+                sv["ctx_ca"] = attention_fwd_dropout(sv["cq"].view(b, q, hd), kv3[:, :, :hd], kv3[:, :, hd:], nh, dh,
+                                                     scale, p_drop, seed + 6).view(b * q, hd)
+            else:
+                sv["ctx_ca"] = ops.mha_small(sv["cq"], sv["kv"][:, :hd], sv["kv"][:, hd:], b, q, n, nh, dh, scale)
             sub = L.ca_out.fwd(sv["ctx_ca"], out_dtype=F32)
         sv["x2"] = _dropout_add(sub, t1_32, p_drop, seed + 2)
         t2_32, t2 = L.n2.fwd(sv["x2"])
@@ -516,7 +546,8 @@ def train_backward(model, st, dlogits, dboxes):
             kv3 = sv["kv"].view(b, n, 2 * hd)
             dkv3 = dkv.view(b, n, 2 * hd)
             attention_bwd(sv["cq"].view(b, q, hd), kv3[:, :, :hd], kv3[:, :, hd:], dctx.view(b, q, hd),
-                          dcq.view(b, q, hd), dkv3[:, :, :hd], dkv3[:, :, hd:], nh, dh, st.scale)
+                          dcq.view(b, q, hd), dkv3[:, :, :hd], dkv3[:, :, hd:], nh, dh, st.scale,
+                          drop_p=p_drop, seed=seed + 6)
             dt1_ca = L.ca_q.bwd(dcq, sv["t1"], grads)
             dm = L.ca_kv.bwd(dkv, st.memory, grads)
             dmem32 = ops.eltwise(ops.ELT_ADD, dmem32, dm, out_dtype=F32)
@@ -527,7 +558,8 @@ def train_backward(model, st, dlogits, dboxes):
         dqkv = torch.empty_like(sv["qkv"])
         qkv3, dq3 = sv["qkv"].view(b, q, -1), dqkv.view(b, q, -1)
         attention_bwd(qkv3[:, :, :hd], qkv3[:, :, hd:2 * hd], qkv3[:, :, 2 * hd:3 * hd], dctx.view(b, q, hd),
-                      dq3[:, :, :hd], dq3[:, :, hd:2 * hd], dq3[:, :, 2 * hd:3 * hd], nh, dh, st.scale)
+                      dq3[:, :, :hd], dq3[:, :, hd:2 * hd], dq3[:, :, 2 * hd:3 * hd], nh, dh, st.scale,
+                      drop_p=p_drop, seed=seed + 5)
         if dqkv.shape[1] > 3 * hd:
             dqkv[:, 3 * hd:].zero_()
         dt0 = L.sa_in.bwd(dqkv, sv["tgt"], grads)

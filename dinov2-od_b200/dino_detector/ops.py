@@ -352,11 +352,12 @@ def softmax_rows(s, n, scale, *, ldp=None, drop_p=0.0, seed=0):
     return p
 
 
-def softmax_bwd_rows(p, dp, n, scale):
+def softmax_bwd_rows(p, dp, n, scale, *, drop_p=0.0, seed=0):
     rows = p.shape[0]
     ds = torch.empty_like(p)
     _dod.call("dod_softmax_bwd_rows", _stream(p), p=p, dp=dp, dp_dtype=_DT[dp.dtype], ds=ds, rows=rows, n=n,
-              ldp=_rowmajor(p, "p"), lddp=_rowmajor(dp, "dp"), ldds=_rowmajor(ds, "ds"), scale=scale)
+              ldp=_rowmajor(p, "p"), lddp=_rowmajor(dp, "dp"), ldds=_rowmajor(ds, "ds"), scale=scale,
+              drop_p=drop_p, seed=seed)
     return ds
 
 

@@ -288,10 +288,12 @@ typedef struct {
   int64_t rows, n, lds, ldp; float scale; float drop_p; int64_t seed;
 } dod_softmax_rows_args;
 DOD_API int32_t dod_softmax_rows(const dod_softmax_rows_args* a, dod_stream_t stream);
-/* dS = scale * P * (dP - rowsum(P * dP)) as bf16 (zero padded to ldds).                        */
+/* dS = scale * P * (dP' - rowsum(P * dP')) as bf16 (zero padded to ldds); P is the probability
+ * before dropout and dP' = dP * keep / (1 - drop_p) with the mask dod_softmax_rows drew for the
+ * same (seed, ldp) -- nn.MultiheadAttention's attention dropout in train mode.                    */
 typedef struct {
   const void* p; const void* dp; int32_t dp_dtype; void* ds;
-  int64_t rows, n, ldp, lddp, ldds; float scale;
+  int64_t rows, n, ldp, lddp, ldds; float scale; float drop_p; int64_t seed;
 } dod_softmax_bwd_rows_args;
 DOD_API int32_t dod_softmax_bwd_rows(const dod_softmax_bwd_rows_args* a, dod_stream_t stream);
 

@@ -115,3 +115,27 @@ def test_attention_backward(b, lq, lk, h, dh):
     assert _rel(dq, qf.grad) < 3e-2
     assert _rel(dk, kf.grad) < 3e-2
     assert _rel(dv, vf.grad) < 3e-2
+
+
+def test_attention_dropout_forward_backward_consistent_with_mask():
+    """Attention-probability dropout: forward and backward use the same counter-hash mask."""
+    from dino_detector import _train, ops
+    g = _g(3)
+    b, lq, lk, h, dh, p_drop, seed = 2, 50, 50, 1, 64, 0.3, 12345
+    q, k, v, do = (_randn((b, n, h * dh), g).bfloat16() for n in (lq, lk, lk, lq))
+    scale = 1 / math.sqrt(dh)
+    lkp = (lk + 7) // 8 * 8
+    ctx = _train.attention_fwd_dropout(q, k, v, h, dh, scale, p_drop, seed)
+    # recover the mask the kernels drew (depends only on seed, row, column)
+    ones = torch.zeros((b * lq, lkp), device="cuda")
+    pd = ops.softmax_rows(ones, lk, 1.0, ldp=lkp, drop_p=p_drop, seed=seed)
+    mask = (pd[:, :lk] > 0).float().view(b, lq, lk)
+    assert abs(mask.mean().item() - (1 - p_drop)) < 0.03
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    P = torch.softmax(qf @ kf.transpose(1, 2) * scale, -1)
+    o = (P * mask / (1 - p_drop)) @ vf
+    assert _rel(ctx, o) < 2e-2
+    o.backward(do.float())
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    _train.attention_bwd(q, k, v, do, dq, dk, dv, h, dh, scale, drop_p=p_drop, seed=seed)
+    assert _rel(dq, qf.grad) < 3e-2 and _rel(dk, kf.grad) < 3e-2 and _rel(dv, vf.grad) < 3e-2
