@@ -58,6 +58,10 @@ def c1():
         m.precision = prec
         with torch.no_grad():
             out[prec + "_ms"] = _timed(lambda: m(x), 20, 3)
+    from dino_detector.runtime import GraphedDetector
+    m.precision = "bf16"
+    graphed = GraphedDetector(m, x)
+    out["bf16_cuda_graph_ms"] = _timed(lambda: graphed(x), 50, 5)
     print(json.dumps({"config": "c1 lightweight S/14 + deformable decoder (100 q), batch 2, 224x224", **out}))
 
 
