@@ -42,6 +42,31 @@ patchify_kernel(const float* __restrict__ pix, __nv_bfloat16* __restrict__ out, 
   }
 }
 
+// uint8 NHWC variant (decoder output of PIL / numpy): fuses ToTensor's /255 (reference
+// train.py:584-587, dataset.py:55-66) into the im2col, so the host->device copy is 1 byte per
+// sample instead of 4.  grid (patch-row, batch); a block walks its 14 image rows, reading the
+// interleaved RGB bytes of a row contiguously.
+__global__ void __launch_bounds__(256)
+patchify_u8_kernel(const uint8_t* __restrict__ pix, __nv_bfloat16* __restrict__ out, int H, int W,
+                   int gh, int gw, int kpad) {
+  const int py = blockIdx.x, b = blockIdx.y;
+  const int wuse = gw * kP * 3;
+  const int64_t row0 = (int64_t(b) * gh + py) * gw;
+  for (int i = 0; i < kP; ++i) {
+    const uint8_t* src = pix + ((int64_t(b) * H + (py * kP + i)) * W) * 3;
+    for (int t = threadIdx.x; t < wuse; t += blockDim.x) {
+      const int x = t / 3, c = t - x * 3;
+      const int px = x / kP, j = x - px * kP;
+      out[(row0 + px) * kpad + c * (kP * kP) + i * kP + j] = __float2bfloat16_rn(float(src[t]) / 255.0f);
+    }
+  }
+  const int padw = kpad - kK;
+  for (int t = threadIdx.x; t < gw * padw; t += blockDim.x) {
+    const int px = t / padw, k = kK + t % padw;
+    out[(row0 + px) * kpad + k] = __float2bfloat16_rn(0.f);
+  }
+}
+
 __global__ void cls_rows_kernel(const float* __restrict__ cls, const float* __restrict__ pos,
                                 float* __restrict__ tokens, int64_t n_tokens, int d) {
   const int b = blockIdx.x;
@@ -104,9 +129,15 @@ extern "C" int32_t dod_patchify14(const dod_patchify_args* a, dod_stream_t strea
   DOD_REQUIRE(a->batch > 0 && gh > 0 && gw > 0, "dod_patchify14: image smaller than one patch");
   DOD_REQUIRE(a->batch <= 65535, "dod_patchify14: batch too large");
   DOD_REQUIRE(a->kpad >= kK && a->kpad % 8 == 0, "dod_patchify14: kpad must be >= 588 and a multiple of 8");
-  patchify_kernel<<<dim3(gh, unsigned(a->batch)), 256, 0, stream>>>(
-      a->pixels, reinterpret_cast<__nv_bfloat16*>(a->patches), int(a->height), int(a->width), gh,
-      gw, int(a->kpad));
+  DOD_REQUIRE(a->pixel_format == 0 || a->pixel_format == 1, "dod_patchify14: bad pixel_format");
+  if (a->pixel_format == 1)
+    patchify_u8_kernel<<<dim3(gh, unsigned(a->batch)), 256, 0, stream>>>(
+        reinterpret_cast<const uint8_t*>(a->pixels), reinterpret_cast<__nv_bfloat16*>(a->patches),
+        int(a->height), int(a->width), gh, gw, int(a->kpad));
+  else
+    patchify_kernel<<<dim3(gh, unsigned(a->batch)), 256, 0, stream>>>(
+        reinterpret_cast<const float*>(a->pixels), reinterpret_cast<__nv_bfloat16*>(a->patches),
+        int(a->height), int(a->width), gh, gw, int(a->kpad));
   int rc = check_cuda(cudaGetLastError(), "patchify_kernel launch");
   if (rc) return rc;
   count_launch();

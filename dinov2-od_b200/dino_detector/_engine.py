@@ -230,9 +230,18 @@ def backbone_forward(pack: BackbonePack, pixel_values, final_norm=True):
     if pixel_values.dim() != 4:
         raise ValueError(f"pixel_values must be [B, 3, H, W], got {tuple(pixel_values.shape)}")
     px = pixel_values.detach()
-    if px.dtype != torch.float32 or not px.is_contiguous():
-        px = px.float().contiguous()
-    b, _, h, w = px.shape
+    if px.dtype == torch.uint8:
+        # raw images, uint8 [B, H, W, 3]: ToTensor's /255 is fused into the im2col kernel (bf16 mode)
+        if mode == "fp32":
+            px = px.permute(0, 3, 1, 2).float().div(255.0).contiguous()
+            b, _, h, w = px.shape
+        else:
+            px = px.contiguous()
+            b, h, w, _ = px.shape
+    else:
+        if px.dtype != torch.float32 or not px.is_contiguous():
+            px = px.float().contiguous()
+        b, _, h, w = px.shape
     gh, gw = h // 14, w // 14
     p, n, d = gh * gw, gh * gw + 1, pack.dim
     m = b * n

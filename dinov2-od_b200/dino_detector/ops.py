@@ -115,9 +115,16 @@ def layernorm(x, gamma, beta, eps, *, out_dtype=torch.bfloat16, also_other=False
 
 
 def patchify14(pixels, kpad, *, cls=None, pos=None, tokens=None):
-    """im2col of 14x14 patches -> bf16 [B*P, kpad]; optionally writes the CLS rows of tokens."""
-    assert pixels.dtype == torch.float32 and pixels.is_contiguous() and pixels.dim() == 4
-    b, c, h, w = pixels.shape
+    """im2col of 14x14 patches -> bf16 [B*P, kpad]; optionally writes the CLS rows of tokens.
+    pixels: f32 [B, 3, H, W] in [0, 1], or uint8 [B, H, W, 3] (0..255, divided by 255 in the kernel)."""
+    assert pixels.is_contiguous() and pixels.dim() == 4
+    if pixels.dtype == torch.uint8:
+        b, h, w, c = pixels.shape
+        fmt = 1
+    else:
+        assert pixels.dtype == torch.float32
+        b, c, h, w = pixels.shape
+        fmt = 0
     if c != 3:
         # same error as HF Dinov2PatchEmbeddings.forward (modeling_dinov2.py:143-147)
         raise ValueError(
@@ -127,7 +134,7 @@ def patchify14(pixels, kpad, *, cls=None, pos=None, tokens=None):
     patches = torch.empty((b * p, kpad), dtype=torch.bfloat16, device=pixels.device)
     _dod.call("dod_patchify14", _stream(pixels), pixels=pixels, patches=patches, batch=b, height=h,
               width=w, kpad=kpad, cls=cls, pos=pos, tokens=tokens,
-              d=tokens.shape[-1] if tokens is not None else 0)
+              d=tokens.shape[-1] if tokens is not None else 0, pixel_format=fmt)
     return patches
 
 

@@ -113,13 +113,15 @@ DOD_API int32_t dod_layernorm(const dod_layernorm_args* a, dod_stream_t stream);
  * Conv2d(3, D, 14, 14) == GEMM over k = c*196 + i*14 + j).  Also writes the
  * CLS rows  x[b*N + 0, :] = cls + pos[0]  (modeling_dinov2.py:108-112).       */
 typedef struct {
-  const float* pixels;  /* f32 [B, 3, H, W]                                   */
+  const void* pixels;   /* pixel_format 0: f32 [B, 3, H, W] in [0, 1]
+                           pixel_format 1: u8  [B, H, W, 3] in 0..255 (ToTensor's /255 fused) */
   void* patches;        /* bf16 [B*P, kpad]  (kpad >= 588, kpad % 8 == 0)      */
   int64_t batch, height, width, kpad;
   const float* cls;     /* f32 [D]                                            */
   const float* pos;     /* f32 [N, D] (already resized to this H, W)          */
   float* tokens;        /* f32 [B*N, D] residual stream; only CLS rows written */
   int64_t d;
+  int32_t pixel_format;
 } dod_patchify_args;
 DOD_API int32_t dod_patchify14(const dod_patchify_args* a, dod_stream_t stream);
 

@@ -80,3 +80,16 @@ def test_channel_mismatch_raises_value_error():
     model, _, _ = build_product_model("c1_small_std", device="cuda")
     with torch.no_grad(), pytest.raises(ValueError):
         model(torch.rand(1, 4, 224, 224).cuda())
+
+
+def test_uint8_nhwc_input_equals_float_input():
+    """Raw uint8 [B, H, W, 3] images (ToTensor's /255 fused into the im2col kernel) give exactly the
+    outputs of the reference-style float [B, 3, H, W] tensor."""
+    model, _, _ = build_product_model("c1_small_std", device="cuda")
+    g = torch.Generator().manual_seed(4)
+    u8 = torch.randint(0, 256, (2, 224, 224, 3), generator=g, dtype=torch.uint8).cuda()
+    xf = u8.permute(0, 3, 1, 2).float().div(255.0).contiguous()
+    with torch.no_grad():
+        a = model(xf)
+        b = model(u8)
+    assert torch.equal(a["pred_logits"], b["pred_logits"]) and torch.equal(a["pred_boxes"], b["pred_boxes"])
