@@ -214,25 +214,50 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
       const int valid = p.seq - j * kTile - half * 64;  // keys valid in this thread's 64 columns
-      // S is read twice from TMEM (row maximum, then exponentials), 32 columns at a time: TMEM
-      // reads are cheap and this keeps the softmax warps under the 96-register budget of 2 CTAs/SM.
+      // kPolyMask == 0 (default): S is read from TMEM once and held in 64 registers.  The polynomial
+      // variants need more live registers than the 96 available with 2 CTAs/SM, so they read S twice
+      // (row maximum, then exponentials), 32 columns at a time.
+      constexpr bool kSinglePass = kPolyMask == 0;
+      uint32_t sraw[kSinglePass ? 2 : 1][32];
       float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
+        uint32_t(&v)[32] = sraw[kSinglePass ? c : 0];
         tmem_ld_32x32(t_lane + kColS + half * 64 + c * 32, v);
-        tmem_ld_wait();
+        if (!kSinglePass || c == 1) tmem_ld_wait();
+        if (kSinglePass && c == 1) {
+          tc_fence_before();
+          mbar_arrive(s_free);  // S_j is in registers: the next Q.K^T may overwrite it
+        }
+        if (!kSinglePass) {
+          if (valid < 64) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= valid) v[i] = 0xff800000u;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            mx0 = fmaxf(mx0, __uint_as_float(v[i]));
+            mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
+          }
+        }
+      }
+      if (kSinglePass) {
         if (valid < 64) {
           // tail tile only (1370 = 10*128 + 90): keys beyond the sequence get -inf
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i >= valid) v[i] = 0xff800000u;
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= valid) sraw[kSinglePass ? c : 0][i] = 0xff800000u;
         }
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          mx0 = fmaxf(mx0, __uint_as_float(v[i]));
-          mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
-        }
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            mx0 = fmaxf(mx0, __uint_as_float(sraw[kSinglePass ? c : 0][i]));
+            mx1 = fmaxf(mx1, __uint_as_float(sraw[kSinglePass ? c : 0][i + 1]));
+          }
       }
       // row maximum over both halves: exchange through shared memory (double buffered by parity)
       float* xm = xmax + (j & 1) * 2 * kTile;
@@ -253,17 +278,19 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
       const float2 nm2 = make_float2(-m_used, -m_used);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_lane + kColS + half * 64 + c * 32, v);
-        tmem_ld_wait();
-        if (c == 1) {
-          tc_fence_before();
-          mbar_arrive(s_free);  // S_j fully consumed: the next Q.K^T may overwrite it
-        }
-        if (valid < 64) {
+        uint32_t(&v)[32] = sraw[kSinglePass ? c : 0];
+        if (!kSinglePass) {
+          tmem_ld_32x32(t_lane + kColS + half * 64 + c * 32, v);
+          tmem_ld_wait();
+          if (c == 1) {
+            tc_fence_before();
+            mbar_arrive(s_free);  // S_j fully consumed: the next Q.K^T may overwrite it
+          }
+          if (valid < 64) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i >= valid) v[i] = 0xff800000u;
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= valid) v[i] = 0xff800000u;
+          }
         }
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
