@@ -119,6 +119,35 @@ int make_tmap_3d(CUtensorMap* out, const void* base, int elt_bytes, uint64_t bat
   return 0;
 }
 
+int make_tmap_4d(CUtensorMap* out, const void* base, int elt_bytes, uint64_t outer, uint64_t inner,
+                 uint64_t rows, uint64_t cols, uint64_t outer_stride, uint64_t inner_stride, uint64_t ld,
+                 uint32_t box_rows, uint32_t box_cols, int swizzle_bytes) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled driver entry point unavailable");
+    return DOD_ERR_CUDA;
+  }
+  cuuint64_t dims[4] = {cols, rows, inner, outer};
+  cuuint64_t strides[3] = {ld * uint64_t(elt_bytes), inner_stride * uint64_t(elt_bytes),
+                           outer_stride * uint64_t(elt_bytes)};
+  cuuint32_t box[4] = {box_cols, box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUtensorMapSwizzle sw = swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                 : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                       : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = fn(out, tmap_dtype(elt_bytes), 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(4d outer=%llu inner=%llu rows=%llu cols=%llu strides=%llu/%llu/%llu) failed: %d",
+              (unsigned long long)outer, (unsigned long long)inner, (unsigned long long)rows,
+              (unsigned long long)cols, (unsigned long long)outer_stride, (unsigned long long)inner_stride,
+              (unsigned long long)ld, int(r));
+    return DOD_ERR_CUDA;
+  }
+  return 0;
+}
+
 }  // namespace dod
 
 extern "C" {

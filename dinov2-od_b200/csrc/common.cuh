@@ -50,6 +50,11 @@ int make_tmap_3d(CUtensorMap* out, const void* base, int elt_bytes,
                  uint64_t bs, uint64_t ld,
                  uint32_t box_rows, uint32_t box_cols, int swizzle_bytes = 128);
 
+// 4-D [outer, inner, rows, cols] view (two batch levels, e.g. image x head); strides in elements.
+int make_tmap_4d(CUtensorMap* out, const void* base, int elt_bytes, uint64_t outer, uint64_t inner,
+                 uint64_t rows, uint64_t cols, uint64_t outer_stride, uint64_t inner_stride, uint64_t ld,
+                 uint32_t box_rows, uint32_t box_cols, int swizzle_bytes = 128);
+
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------
 // device helpers
@@ -146,6 +151,22 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
+                                            int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0),
+      "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int32_t c0,
+                                             int32_t c1, int32_t c2, int32_t c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 // smem -> global tile store (bulk async group) and its completion waits
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c0,
                                              int32_t c1) {
@@ -183,6 +204,17 @@ __device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const CUtensorMa
       " [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar_cluster_addr), "r"(c0),
       "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const CUtensorMap* m,
+                                                uint32_t mbar_cluster_addr, int32_t c0, int32_t c1,
+                                                int32_t c2, int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(mbar_cluster_addr), "r"(c0),
+      "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 

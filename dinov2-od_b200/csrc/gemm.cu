@@ -45,7 +45,7 @@ constexpr int kChunkBytes = 32 * 64;  // one epilogue chunk buffer: 32 rows x 64
 
 struct GemmParams {
   int M, N, K1blocks, K2blocks;
-  int tiles_m, tiles_n, batch;
+  int tiles_m, tiles_n, batch, batch_inner;
   const float* bias;
   const float* scale;
   const float* residual;
@@ -56,6 +56,24 @@ struct GemmParams {
   int out_f32;
   int patch_rows;
   int direct;  // 1: register -> global epilogue (patch rows / shapes TMA cannot store)
+};
+
+// two batch levels (outer x inner) of a problem; a level that is not used still needs a valid
+// (16-byte multiple, non-zero) TMA stride
+struct BatchDims {
+  uint64_t outer, inner, os_a, os_w, os_o, is_a, is_w, is_o;
+  explicit BatchDims(const dod_gemm_args& a) {
+    outer = a.batch > 1 ? uint64_t(a.batch) : 1;
+    inner = a.batch_inner > 1 ? uint64_t(a.batch_inner) : 1;
+    const int64_t n_out = a.act == DOD_ACT_SWIGLU ? a.n / 2 : a.n;
+    (void)n_out;
+    is_a = inner > 1 ? uint64_t(a.inner_stride_a) : uint64_t(a.m) * a.lda;
+    is_w = inner > 1 ? uint64_t(a.inner_stride_w) : uint64_t(a.n) * a.ldw;
+    is_o = inner > 1 ? uint64_t(a.inner_stride_out) : uint64_t(a.m) * a.ldo;
+    os_a = outer > 1 ? uint64_t(a.batch_stride_a) : uint64_t(a.m) * a.lda;
+    os_w = outer > 1 ? uint64_t(a.batch_stride_w) : uint64_t(a.n) * a.ldw;
+    os_o = outer > 1 ? uint64_t(a.batch_stride_out) : uint64_t(a.m) * a.ldo;
+  }
 };
 
 template <int BN, bool RES>
@@ -248,7 +266,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0 && in_range && row0 < p.M) {
-      tma_store_3d(tm_out, ob, n0, row0, bz);
+      tma_store_4d(tm_out, ob, n0, row0, bz % p.batch_inner, bz / p.batch_inner);
       tma_store_commit();
     }
   }
@@ -411,8 +429,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
           uint8_t* sb = sa + L::kStageA;
           mbar_expect_tx(&full[s], L::kStage);
           if (kb < p.K1blocks) {
-            tma_load_3d(sa, &tm_a, &full[s], kb * BK, mb * BM, bz);
-            tma_load_3d(sb, &tm_w, &full[s], kb * BK, nb * BN, bz);
+            tma_load_4d(sa, &tm_a, &full[s], kb * BK, mb * BM, bz % p.batch_inner, bz / p.batch_inner);
+            tma_load_4d(sb, &tm_w, &full[s], kb * BK, nb * BN, bz % p.batch_inner, bz / p.batch_inner);
           } else {
             tma_load_2d(sa, &tm_a2, &full[s], (kb - p.K1blocks) * BK, mb * BM);
             tma_load_2d(sb, &tm_w2, &full[s], (kb - p.K1blocks) * BK, nb * BN);
@@ -596,8 +614,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
           const uint32_t full_leader = map_to_cta(&full[s], 0);
           if (rank == 0) mbar_expect_tx(&full[s], 2 * L::kStage);  // bytes of both CTAs
           if (kb < p.K1blocks) {
-            tma_load_3d_2sm(sa, &tm_a, full_leader, kb * BK, row_a, bz);
-            tma_load_3d_2sm(sb, &tm_w, full_leader, kb * BK, row_w, bz);
+            tma_load_4d_2sm(sa, &tm_a, full_leader, kb * BK, row_a, bz % p.batch_inner, bz / p.batch_inner);
+            tma_load_4d_2sm(sb, &tm_w, full_leader, kb * BK, row_w, bz % p.batch_inner, bz / p.batch_inner);
           } else {
             tma_load_3d_2sm(sa, &tm_a2, full_leader, (kb - p.K1blocks) * BK, row_a, 0);
             tma_load_3d_2sm(sb, &tm_w2, full_leader, (kb - p.K1blocks) * BK, row_w, 0);
@@ -684,11 +702,9 @@ int launch2(const dod_gemm_args& a, cudaStream_t stream) {
     attr_set = true;
   }
   CUtensorMap tm_a, tm_w, tm_a2, tm_w2, tm_out, tm_res;
-  const uint64_t nbatch = a.batch > 1 ? uint64_t(a.batch) : 1;
-  const uint64_t bs_a = nbatch > 1 ? uint64_t(a.batch_stride_a) : uint64_t(a.m) * a.lda;
-  const uint64_t bs_w = nbatch > 1 ? uint64_t(a.batch_stride_w) : uint64_t(a.n) * a.ldw;
-  if (int rc = make_tmap_3d(&tm_a, a.a, 2, nbatch, a.m, a.k, bs_a, a.lda, 128, BK, 128)) return rc;
-  if (int rc = make_tmap_3d(&tm_w, a.w, 2, nbatch, a.n, a.k, bs_w, a.ldw, 128, BK, 128)) return rc;
+  const BatchDims bd(a);
+  if (int rc = make_tmap_4d(&tm_a, a.a, 2, bd.outer, bd.inner, a.m, a.k, bd.os_a, bd.is_a, a.lda, 128, BK, 128)) return rc;
+  if (int rc = make_tmap_4d(&tm_w, a.w, 2, bd.outer, bd.inner, a.n, a.k, bd.os_w, bd.is_w, a.ldw, 128, BK, 128)) return rc;
   if (a.a2) {
     if (int rc = make_tmap_3d(&tm_a2, a.a2, 2, 1, a.m, a.k2, uint64_t(a.m) * a.lda2, a.lda2, 128, BK, 128)) return rc;
     if (int rc = make_tmap_3d(&tm_w2, a.w2, 2, 1, a.n, a.k2, uint64_t(a.n) * a.ldw2, a.ldw2, 128, BK, 128)) return rc;
@@ -698,9 +714,8 @@ int launch2(const dod_gemm_args& a, cudaStream_t stream) {
   }
   const bool out_f32 = a.out_dtype == DOD_F32;
   const int64_t n_out = a.act == DOD_ACT_SWIGLU ? a.n / 2 : a.n;
-  const uint64_t bs_o = nbatch > 1 ? uint64_t(a.batch_stride_out) : uint64_t(a.m) * a.ldo;
-  if (int rc = make_tmap_3d(&tm_out, a.out, out_f32 ? 4 : 2, nbatch, a.m, n_out, bs_o, a.ldo, 32,
-                            out_f32 ? 16 : 32, 64))
+  if (int rc = make_tmap_4d(&tm_out, a.out, out_f32 ? 4 : 2, bd.outer, bd.inner, a.m, n_out, bd.os_o, bd.is_o,
+                            a.ldo, 32, out_f32 ? 16 : 32, 64))
     return rc;
   if (RES) {
     if (int rc = make_tmap_2d(&tm_res, a.residual, 4, a.m, a.n, a.ldr, 32, 16, 64)) return rc;
@@ -714,7 +729,8 @@ int launch2(const dod_gemm_args& a, cudaStream_t stream) {
   p.K2blocks = a.a2 ? int((a.k2 + BK - 1) / BK) : 0;
   p.tiles_m = int((a.m + 255) / 256);
   p.tiles_n = int((a.n + 255) / 256);
-  p.batch = int(nbatch);
+  p.batch = int(bd.outer * bd.inner);
+  p.batch_inner = int(bd.inner);
   p.bias = a.bias;
   p.scale = a.scale;
   p.residual = reinterpret_cast<const float*>(a.residual);
@@ -741,12 +757,9 @@ int launch(const dod_gemm_args& a, cudaStream_t stream, bool direct) {
     attr_set = true;
   }
   CUtensorMap tm_a, tm_w, tm_a2, tm_w2, tm_out, tm_res;
-  const uint64_t nbatch = a.batch > 1 ? uint64_t(a.batch) : 1;
-  // batch stride of a single problem only has to be a valid (16-byte multiple) TMA stride
-  const uint64_t bs_a = nbatch > 1 ? uint64_t(a.batch_stride_a) : uint64_t(a.m) * a.lda;
-  const uint64_t bs_w = nbatch > 1 ? uint64_t(a.batch_stride_w) : uint64_t(a.n) * a.ldw;
-  if (int rc = make_tmap_3d(&tm_a, a.a, 2, nbatch, a.m, a.k, bs_a, a.lda, BM, BK, 128)) return rc;
-  if (int rc = make_tmap_3d(&tm_w, a.w, 2, nbatch, a.n, a.k, bs_w, a.ldw, BN, BK, 128)) return rc;
+  const BatchDims bd(a);
+  if (int rc = make_tmap_4d(&tm_a, a.a, 2, bd.outer, bd.inner, a.m, a.k, bd.os_a, bd.is_a, a.lda, BM, BK, 128)) return rc;
+  if (int rc = make_tmap_4d(&tm_w, a.w, 2, bd.outer, bd.inner, a.n, a.k, bd.os_w, bd.is_w, a.ldw, BN, BK, 128)) return rc;
   if (a.a2) {
     if (int rc = make_tmap_2d(&tm_a2, a.a2, 2, a.m, a.k2, a.lda2, BM, BK)) return rc;
     if (int rc = make_tmap_2d(&tm_w2, a.w2, 2, a.n, a.k2, a.ldw2, BN, BK)) return rc;
@@ -757,9 +770,8 @@ int launch(const dod_gemm_args& a, cudaStream_t stream, bool direct) {
   const bool out_f32 = a.out_dtype == DOD_F32;
   const int64_t n_out = a.act == DOD_ACT_SWIGLU ? a.n / 2 : a.n;
   if (!direct) {
-    const uint64_t bs_o = nbatch > 1 ? uint64_t(a.batch_stride_out) : uint64_t(a.m) * a.ldo;
-    if (int rc = make_tmap_3d(&tm_out, a.out, out_f32 ? 4 : 2, nbatch, a.m, n_out, bs_o, a.ldo, 32,
-                              out_f32 ? 16 : 32, 64))
+    if (int rc = make_tmap_4d(&tm_out, a.out, out_f32 ? 4 : 2, bd.outer, bd.inner, a.m, n_out, bd.os_o,
+                              bd.is_o, a.ldo, 32, out_f32 ? 16 : 32, 64))
       return rc;
   } else {
     tm_out = tm_a;
@@ -776,7 +788,8 @@ int launch(const dod_gemm_args& a, cudaStream_t stream, bool direct) {
   p.K2blocks = a.a2 ? int((a.k2 + BK - 1) / BK) : 0;
   p.tiles_m = int((a.m + BM - 1) / BM);
   p.tiles_n = int((a.n + BN - 1) / BN);
-  p.batch = int(nbatch);
+  p.batch = int(bd.outer * bd.inner);
+  p.batch_inner = int(bd.inner);
   p.bias = a.bias;
   p.scale = a.scale;
   p.residual = reinterpret_cast<const float*>(a.residual);
@@ -846,6 +859,14 @@ extern "C" int32_t dod_gemm_bf16(const dod_gemm_args* a, dod_stream_t stream_) {
                 "dod_gemm_bf16: a2/w2 must be 16-byte aligned");
   }
   DOD_REQUIRE(a->act >= DOD_ACT_NONE && a->act <= DOD_ACT_SWIGLU, "dod_gemm_bf16: bad act");
+  if (a->batch_inner > 1) {
+    DOD_REQUIRE(a->inner_stride_a % 8 == 0 && a->inner_stride_w % 8 == 0 &&
+                    a->inner_stride_out % (a->out_dtype == DOD_F32 ? 4 : 8) == 0 && a->inner_stride_a > 0 &&
+                    a->inner_stride_w > 0 && a->inner_stride_out > 0,
+                "dod_gemm_bf16: inner batch strides must be positive multiples of 16 bytes");
+    DOD_REQUIRE(!a->residual && !a->a2 && a->patch_rows == 0,
+                "dod_gemm_bf16: batched problems take no residual / second K segment / patch rows");
+  }
   if (a->batch > 1) {
     DOD_REQUIRE(!a->residual && !a->a2 && a->patch_rows == 0,
                 "dod_gemm_bf16: batched problems take no residual / second K segment / patch rows");
@@ -853,7 +874,8 @@ extern "C" int32_t dod_gemm_bf16(const dod_gemm_args* a, dod_stream_t stream_) {
                     a->batch_stride_out % (a->out_dtype == DOD_F32 ? 4 : 8) == 0 &&
                     a->batch_stride_a > 0 && a->batch_stride_w > 0 && a->batch_stride_out > 0,
                 "dod_gemm_bf16: batch strides must be positive multiples of 16 bytes");
-    DOD_REQUIRE(a->batch * ((a->m + 127) / 128) * ((a->n + 63) / 64) < (1ll << 31),
+    DOD_REQUIRE(a->batch * (a->batch_inner > 1 ? a->batch_inner : 1) * ((a->m + 127) / 128) *
+                        ((a->n + 63) / 64) < (1ll << 31),
                 "dod_gemm_bf16: too many tiles");
   }
   DOD_REQUIRE(a->out_dtype == DOD_BF16 || a->out_dtype == DOD_F32, "dod_gemm_bf16: bad out_dtype");

@@ -29,11 +29,12 @@ __device__ __forceinline__ void stv(void* p, int64_t i, int dt, float v) {
 // ------------------------------------------------------------------ transpose
 __global__ void __launch_bounds__(256)
 transpose_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int rows,
-                 int cols, int64_t ld_in, int64_t ld_out, int64_t bs_in, int64_t bs_out) {
+                 int cols, int64_t ld_in, int64_t ld_out, int64_t bs_in, int64_t bs_out, int inner,
+                 int64_t is_in) {
   __shared__ __nv_bfloat16 tile[64][66];
-  const int b = blockIdx.z;
+  const int b = blockIdx.z;  // outer * inner + inner index; the output is contiguous over both
   const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
-  const __nv_bfloat16* ip = in + int64_t(b) * bs_in;
+  const __nv_bfloat16* ip = in + int64_t(b / inner) * bs_in + int64_t(b % inner) * is_in;
   __nv_bfloat16* op = out + int64_t(b) * bs_out;
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
   for (int r = ty; r < 64; r += 4) {
@@ -413,11 +414,14 @@ extern "C" int32_t dod_transpose_bf16(const dod_transpose_args* a, dod_stream_t 
   DOD_REQUIRE(a->rows > 0 && a->cols > 0 && a->batch > 0 && a->batch <= 65535 && a->ld_in >= a->cols &&
                   a->ld_out >= a->rows,
               "dod_transpose_bf16: bad shape");
-  dim3 grid(unsigned((a->cols + 63) / 64), unsigned((a->rows + 63) / 64), unsigned(a->batch));
+  const int64_t inner = a->batch_inner > 1 ? a->batch_inner : 1;
+  DOD_REQUIRE(a->batch * inner <= 65535, "dod_transpose_bf16: too many batches");
+  dim3 grid(unsigned((a->cols + 63) / 64), unsigned((a->rows + 63) / 64), unsigned(a->batch * inner));
   DOD_REQUIRE(grid.y <= 65535, "dod_transpose_bf16: too many rows");
   transpose_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)a->in, (__nv_bfloat16*)a->out,
                                             int(a->rows), int(a->cols), a->ld_in, a->ld_out,
-                                            a->batch_stride_in, a->batch_stride_out);
+                                            a->batch_stride_in, a->batch_stride_out, int(inner),
+                                            a->inner_stride_in);
   int rc = check_cuda(cudaGetLastError(), "transpose_kernel launch");
   if (rc == 0) count_launch();
   return rc;

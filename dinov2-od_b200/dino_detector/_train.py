@@ -161,45 +161,49 @@ class LLinear:
 # ---------------------------------------------------------------------------
 # attention backward (materialised probabilities, batched tcgen05 GEMMs)
 # ---------------------------------------------------------------------------
+def _heads(x3, heads, dh):
+    """[B, L, H*dh] (strided, unit inner stride) -> [B, H, L, dh] view, no copy."""
+    b, l, _ = x3.shape
+    return x3.as_strided((b, heads, l, dh), (x3.stride(0), dh, x3.stride(1), 1), x3.storage_offset())
+
+
 def attention_fwd_dropout(q3, k3, v3, heads, dh, scale, drop_p, seed):
     """Materialised attention forward with dropout on the probabilities (nn.MultiheadAttention in
-    train mode): ctx = dropout(softmax(Q K^T * scale)) V, per head with the batched GEMM."""
+    train mode): ctx = dropout(softmax(Q K^T * scale)) V, all heads in one batched GEMM each."""
     b, lq, d = q3.shape
     lk = k3.shape[1]
     lkp = _pad8(lk)
+    q4, k4, v4 = _heads(q3, heads, dh), _heads(k3, heads, dh), _heads(v3, heads, dh)
     ctx = torch.empty((b, lq, d), dtype=BF16, device=q3.device)
-    for h in range(heads):
-        sl = slice(h * dh, (h + 1) * dh)
-        s_full = torch.empty((b, lq, lkp), dtype=F32, device=q3.device)
-        ops.gemm_batched(q3[:, :, sl], k3[:, :, sl], s_full[:, :, :lk])
-        pd = ops.softmax_rows(s_full.view(b * lq, lkp), lk, scale, ldp=lkp, drop_p=drop_p, seed=seed + (h << 24))
-        ops.gemm_batched(pd.view(b, lq, lkp)[:, :, :lk], ops.transpose(v3[:, :, sl]), ctx[:, :, sl])
+    s_full = torch.empty((b, heads, lq, lkp), dtype=F32, device=q3.device)
+    ops.gemm_batched(q4, k4, s_full[..., :lk])
+    pd = ops.softmax_rows(s_full.view(-1, lkp), lk, scale, ldp=lkp, drop_p=drop_p, seed=seed)
+    ops.gemm_batched(pd.view(b, heads, lq, lkp)[..., :lk], ops.transpose(v4), _heads(ctx, heads, dh))
     return ctx
 
 
 def attention_bwd(q3, k3, v3, dctx3, dq3, dk3, dv3, heads, dh, scale, drop_p=0.0, seed=0):
     """q3 [B, Lq, H*dh], k3/v3 [B, Lk, H*dh], dctx3 [B, Lq, H*dh] (bf16 3-D views, unit inner
-    stride); writes bf16 gradients into the dq3/dk3/dv3 views.  drop_p/seed: the attention dropout
-    mask of attention_fwd_dropout is regenerated from the counter hash."""
+    stride); writes bf16 gradients into the dq3/dk3/dv3 views.  All (image, head) problems run as
+    ONE batched tcgen05 GEMM per product through 4-D TMA maps over the head-strided views.
+    drop_p/seed: the attention dropout mask of attention_fwd_dropout is regenerated from the hash."""
     b, lq, _ = q3.shape
     lk = k3.shape[1]
     lkp = _pad8(lk)
     dev = q3.device
-    for h in range(heads):
-        sl = slice(h * dh, (h + 1) * dh)
-        hseed = seed + (h << 24)
-        qh, kh, vh, doh = q3[:, :, sl], k3[:, :, sl], v3[:, :, sl], dctx3[:, :, sl]
-        s_full = torch.empty((b, lq, lkp), dtype=F32, device=dev)
-        ops.gemm_batched(qh, kh, s_full[:, :, :lk])                                  # S = Q K^T
-        p = ops.softmax_rows(s_full.view(b * lq, lkp), lk, scale, ldp=lkp)           # P  [B*Lq, lkp]
-        pd = p if drop_p <= 0 else ops.softmax_rows(s_full.view(b * lq, lkp), lk, scale, ldp=lkp,
-                                                     drop_p=drop_p, seed=hseed)      # dropout(P)
-        ops.gemm_batched(doh, vh, s_full[:, :, :lk])                                 # dP = dO V^T
-        ds = ops.softmax_bwd_rows(p, s_full.view(b * lq, lkp), lk, scale, drop_p=drop_p, seed=hseed)
-        ds3, pd3 = ds.view(b, lq, lkp)[:, :, :lk], pd.view(b, lq, lkp)[:, :, :lk]
-        ops.gemm_batched(ds3, ops.transpose(kh), dq3[:, :, sl])                      # dQ = dS K
-        ops.gemm_batched(ops.transpose(ds3), ops.transpose(qh), dk3[:, :, sl])       # dK = dS^T Q
-        ops.gemm_batched(ops.transpose(pd3), ops.transpose(doh), dv3[:, :, sl])      # dV = dropout(P)^T dO
+    q4, k4, v4, do4 = (_heads(t, heads, dh) for t in (q3, k3, v3, dctx3))
+    s_full = torch.empty((b, heads, lq, lkp), dtype=F32, device=dev)
+    s2d = s_full.view(-1, lkp)
+    ops.gemm_batched(q4, k4, s_full[..., :lk])                                       # S = Q K^T
+    p = ops.softmax_rows(s2d, lk, scale, ldp=lkp)                                    # P  [B*H*Lq, lkp]
+    pd = p if drop_p <= 0 else ops.softmax_rows(s2d, lk, scale, ldp=lkp, drop_p=drop_p, seed=seed)
+    ops.gemm_batched(do4, v4, s_full[..., :lk])                                      # dP = dO V^T
+    ds = ops.softmax_bwd_rows(p, s2d, lk, scale, drop_p=drop_p, seed=seed)           # dS
+    ds4 = ds.view(b, heads, lq, lkp)[..., :lk]
+    pd4 = pd.view(b, heads, lq, lkp)[..., :lk]
+    ops.gemm_batched(ds4, ops.transpose(k4), _heads(dq3, heads, dh))                 # dQ = dS K
+    ops.gemm_batched(ops.transpose(ds4), ops.transpose(q4), _heads(dk3, heads, dh))  # dK = dS^T Q
+    ops.gemm_batched(ops.transpose(pd4), ops.transpose(do4), _heads(dv3, heads, dh))  # dV = dropout(P)^T dO
 
 
 # ---------------------------------------------------------------------------

@@ -267,36 +267,51 @@ ELT_CAST, ELT_SCALE_COLS, ELT_ADD, ELT_GELU_FWD, ELT_GELU_BWD, ELT_RELU_BWD, ELT
 
 
 def gemm_batched(a, w, out, *, bias=None, act=ACT_NONE):
-    """out[b] = act(a[b] @ w[b].T + bias): a [B, M, K], w [B, N, K], out [B, M, N]; 3-D views with
-    unit inner stride and row / batch strides that are multiples of 8 elements."""
+    """out[..] = act(a[..] @ w[..].T + bias) over one or two leading batch dims:
+    a [B, M, K] / [B, H, M, K], w [B, N, K] / [B, H, N, K], out [B, M, N] / [B, H, M, N]; strided views
+    with unit inner stride and row / batch strides that are multiples of 8 elements (e.g. head slices
+    of a fused qkv buffer viewed as [B, H, L, dh])."""
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
-    assert a.dim() == 3 and w.dim() == 3 and out.dim() == 3
-    assert a.stride(2) == 1 and w.stride(2) == 1 and out.stride(2) == 1
-    nb, m, k = a.shape
-    n = w.shape[1]
-    assert w.shape[0] == nb and w.shape[2] == k and tuple(out.shape) == (nb, m, n), (a.shape, w.shape, out.shape)
-    with _Timed("gemm", 2.0 * nb * m * n * k):
-        _dod.call("dod_gemm_bf16", _stream(a), a=a, w=w, m=m, n=n, k=k, lda=a.stride(1), ldw=w.stride(1),
-                  bias=bias, act=act, out=out, ldo=out.stride(1), out_dtype=_DT[out.dtype], batch=nb,
+    assert a.dim() == w.dim() == out.dim() and a.dim() in (3, 4)
+    assert a.stride(-1) == 1 and w.stride(-1) == 1 and out.stride(-1) == 1
+    if a.dim() == 3:
+        a, w, out = a.unsqueeze(1), w.unsqueeze(1), out.unsqueeze(1)
+    nb, nh, m, k = a.shape
+    n = w.shape[2]
+    assert tuple(w.shape) == (nb, nh, n, k) and tuple(out.shape) == (nb, nh, m, n), (a.shape, w.shape, out.shape)
+    with _Timed("gemm", 2.0 * nb * nh * m * n * k):
+        _dod.call("dod_gemm_bf16", _stream(a), a=a, w=w, m=m, n=n, k=k, lda=a.stride(2), ldw=w.stride(2),
+                  bias=bias, act=act, out=out, ldo=out.stride(2), out_dtype=_DT[out.dtype], batch=nb,
                   batch_stride_a=a.stride(0) if nb > 1 else 0, batch_stride_w=w.stride(0) if nb > 1 else 0,
-                  batch_stride_out=out.stride(0) if nb > 1 else 0)
+                  batch_stride_out=out.stride(0) if nb > 1 else 0, batch_inner=nh,
+                  inner_stride_a=a.stride(1) if nh > 1 else 0, inner_stride_w=w.stride(1) if nh > 1 else 0,
+                  inner_stride_out=out.stride(1) if nh > 1 else 0)
     return out
 
 
 def transpose(x, out=None):
-    """bf16 [.., R, C] -> [.., C, R] (2-D or batched 3-D views with unit inner stride); the result's
-    row stride is padded to a multiple of 8 so it can feed the GEMM."""
+    """bf16 [.., R, C] -> [.., C, R] for 2-D, 3-D [B, R, C] or 4-D [B, H, R, C] strided views with unit
+    inner stride; the result is contiguous over the batch dims with its row stride padded to a multiple
+    of 8 so it can feed the GEMM."""
     assert x.dtype == torch.bfloat16 and x.stride(-1) == 1
-    x3 = x.unsqueeze(0) if x.dim() == 2 else x
-    nb, r, c = x3.shape
+    dims = x.dim()
+    x4 = x if dims == 4 else (x.unsqueeze(0) if dims == 3 else x.unsqueeze(0).unsqueeze(0))
+    if dims == 3:
+        x4 = x.unsqueeze(1)
+    nb, nh, r, c = x4.shape
     if out is None:
-        out = torch.empty((nb, c, (r + 7) // 8 * 8), dtype=torch.bfloat16, device=x.device)[:, :, :r]
-    o3 = out if out.dim() == 3 else out.unsqueeze(0)
-    _dod.call("dod_transpose_bf16", _stream(x), **{"in": x3, "out": o3, "rows": r, "cols": c,
-                                                 "ld_in": x3.stride(1), "ld_out": o3.stride(1), "batch": nb,
-                                                 "batch_stride_in": x3.stride(0),
-                                                 "batch_stride_out": o3.stride(0)})
-    return o3 if x.dim() == 3 else o3[0]
+        out = torch.empty((nb, nh, c, (r + 7) // 8 * 8), dtype=torch.bfloat16, device=x.device)[:, :, :, :r]
+    o4 = out
+    while o4.dim() < 4:
+        o4 = o4.unsqueeze(0) if o4.dim() == 2 else o4.unsqueeze(1)
+    _dod.call("dod_transpose_bf16", _stream(x), **{"in": x4, "out": o4, "rows": r, "cols": c,
+                                                 "ld_in": x4.stride(2), "ld_out": o4.stride(2), "batch": nb,
+                                                 "batch_stride_in": x4.stride(0),
+                                                 "batch_stride_out": o4.stride(1),
+                                                 "batch_inner": nh, "inner_stride_in": x4.stride(1)})
+    if dims == 4:
+        return o4
+    return o4[:, 0] if dims == 3 else o4[0, 0]
 
 
 def lowrank_wgrad(big, small, r, out, *, transposed, alpha=1.0):

@@ -88,6 +88,10 @@ typedef struct {
    * independent GEMMs whose A / W / out start batch_stride_* ELEMENTS apart (multiples of 8).
    * batch <= 1 (or 0) is the plain 2-D problem.  No residual / a2 / patch_rows when batched.  */
   int64_t batch, batch_stride_a, batch_stride_w, batch_stride_out;
+  /* second (inner) batch level, e.g. attention heads inside an image: batch_inner > 1 runs
+   * batch * batch_inner problems; problem (bo, bi) starts at bo * batch_stride_* + bi * inner_stride_*.
+   * Strides are in elements and multiples of 8 (16 bytes); 0 / 1 = no inner level.                    */
+  int64_t batch_inner, inner_stride_a, inner_stride_w, inner_stride_out;
 } dod_gemm_args;
 DOD_API int32_t dod_gemm_bf16(const dod_gemm_args* a, dod_stream_t stream);
 
@@ -230,6 +234,9 @@ DOD_API int32_t dod_split3_bf16(const dod_split3_args* a, dod_stream_t stream);
 typedef struct {
   const void* in; void* out;             /* bf16 [batch, rows, cols] -> [batch, cols, rows]     */
   int64_t rows, cols, ld_in, ld_out, batch, batch_stride_in, batch_stride_out;
+  /* optional inner batch level (heads): input (bo, bi) at bo*batch_stride_in + bi*inner_stride_in,
+   * output index bo*batch_inner + bi with stride batch_stride_out                               */
+  int64_t batch_inner, inner_stride_in;
 } dod_transpose_args;
 DOD_API int32_t dod_transpose_bf16(const dod_transpose_args* a, dod_stream_t stream);
 

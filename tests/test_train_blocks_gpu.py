@@ -128,7 +128,7 @@ def test_attention_dropout_forward_backward_consistent_with_mask():
     ctx = _train.attention_fwd_dropout(q, k, v, h, dh, scale, p_drop, seed)
     # recover the mask the kernels drew (depends only on seed, row, column)
     ones = torch.zeros((b * lq, lkp), device="cuda")
-    pd = ops.softmax_rows(ones, lk, 1.0, ldp=lkp, drop_p=p_drop, seed=seed)
+    pd = ops.softmax_rows(ones, lk, 1.0, ldp=lkp, drop_p=p_drop, seed=seed)   # rows = (b, h=0, q)
     mask = (pd[:, :lk] > 0).float().view(b, lq, lk)
     assert abs(mask.mean().item() - (1 - p_drop)) < 0.03
     qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))

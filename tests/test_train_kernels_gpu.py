@@ -44,6 +44,32 @@ def test_gemm_batched_strided_heads(ops):
         assert _rel(out, ref) < 2e-5
 
 
+def test_gemm_batched_two_levels(ops):
+    """All (image, head) problems in one launch through head-strided 4-D views."""
+    g = _g(3)
+    b, s, h = 2, 300, 3
+    d = h * 64
+    qkv = _randn((b * s, 3 * d), g).bfloat16()
+    q3 = qkv.view(b, s, 3 * d)
+    q4 = q3[:, :, :d].as_strided((b, h, s, 64), (s * 3 * d, 64, 3 * d, 1), q3[:, :, :d].storage_offset())
+    k4 = q3[:, :, d:2 * d].as_strided((b, h, s, 64), (s * 3 * d, 64, 3 * d, 1), q3[:, :, d:2 * d].storage_offset())
+    sp = (s + 7) // 8 * 8
+    out = torch.empty((b, h, s, sp), dtype=torch.float32, device="cuda")
+    ops.gemm_batched(q4, k4, out[..., :s])
+    ref = q4.float() @ k4.float().transpose(-1, -2)
+    assert _rel(out[..., :s], ref) < 2e-5
+    t = ops.transpose(k4)
+    assert t.shape == (b, h, 64, s) and torch.equal(t, k4.transpose(-1, -2))
+    # strided bf16 output into head slices of a [B, L, D] buffer
+    dst = torch.zeros((b, s, d), dtype=torch.bfloat16, device="cuda")
+    d4 = dst.as_strided((b, h, s, 64), (s * d, 64, d, 1), 0)
+    p_full = torch.zeros((b, h, s, sp), dtype=torch.bfloat16, device="cuda")     # row stride % 8 == 0
+    p_full[..., :s] = torch.softmax(ref, -1).bfloat16()
+    p = p_full[..., :s]
+    ops.gemm_batched(p, ops.transpose(k4), d4)
+    assert _rel(d4, p.float() @ k4.float()) < 1e-2
+
+
 def test_transpose(ops):
     g = _g(1)
     x = _randn((3, 257, 100), g).bfloat16()
