@@ -121,8 +121,10 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
       mbar_init(&v_empty[s], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(s_free, kSoftmaxThreads);
-    mbar_init(p_full, kSoftmaxThreads);
+    // one elected lane per softmax warp arrives (after __syncwarp): 256 per-thread arrivals on one
+    // shared-memory word serialise (~32 cycles per warp) and sat on the critical path of every tile
+    mbar_init(s_free, kSoftmaxThreads / 32);
+    mbar_init(p_full, kSoftmaxThreads / 32);
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
@@ -217,17 +219,23 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
       // kPolyMask == 0 (default): S is read from TMEM once and held in 64 registers.  The polynomial
       // variants need more live registers than the 96 available with 2 CTAs/SM, so they read S twice
       // (row maximum, then exponentials), 32 columns at a time.
-      constexpr bool kSinglePass = kPolyMask == 0 || kPolyMask == 0x100;
+      constexpr bool kSinglePass = kPolyMask == 0 || kPolyMask >= 0x100;
+      constexpr bool kProbeNoLoad = kPolyMask == 0x200;  // timing experiment: skip the TMEM read of S
       uint32_t sraw[kSinglePass ? 2 : 1][32];
       float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t(&v)[32] = sraw[kSinglePass ? c : 0];
-        tmem_ld_32x32(t_lane + kColS + half * 64 + c * 32, v);
+        if (!kProbeNoLoad) tmem_ld_32x32(t_lane + kColS + half * 64 + c * 32, v);
+        else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(float(row + i + j) * 1e-3f);
+        }
         if (!kSinglePass || c == 1) tmem_ld_wait();
         if (kSinglePass && c == 1) {
           tc_fence_before();
-          mbar_arrive(s_free);  // S_j is in registers: the next Q.K^T may overwrite it
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_free);  // S_j is in registers: the next Q.K^T may overwrite it
         }
         if (!kSinglePass) {
           if (valid < 64) {
@@ -284,7 +292,8 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
           tmem_ld_wait();
           if (c == 1) {
             tc_fence_before();
-            mbar_arrive(s_free);  // S_j fully consumed: the next Q.K^T may overwrite it
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_free);  // S_j fully consumed: the next Q.K^T may overwrite it
           }
           if (valid < 64) {
 #pragma unroll
@@ -323,7 +332,8 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
       tmem_st_32x32(t_lane + kColP + half * 32, pk);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(p_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
     }
 
     // ---- epilogue: O / l -> ctx ----
@@ -385,6 +395,7 @@ extern "C" int32_t dod_fmha_fwd(const dod_fmha_args* a, dod_stream_t stream_) {
     DOD_CUDA_OK(cudaFuncSetAttribute(fmha_kernel<0x52>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     DOD_CUDA_OK(cudaFuncSetAttribute(fmha_kernel<0x5a>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     DOD_CUDA_OK(cudaFuncSetAttribute(fmha_kernel<0x100>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    DOD_CUDA_OK(cudaFuncSetAttribute(fmha_kernel<0x200>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   }
   CUtensorMap tm;
   if (int rc = make_tmap_3d(&tm, a->qkv, 2, a->batch, a->seq, a->ld, a->seq * a->ld, a->ld, kTile, kD))
@@ -403,6 +414,7 @@ extern "C" int32_t dod_fmha_fwd(const dod_fmha_args* a, dod_stream_t stream_) {
   else if (poly == 2) fmha_kernel<0x12><<<grid, kThreads, kSmemBytes, stream>>>(tm, p);
   else if (poly == 4) fmha_kernel<0x5a><<<grid, kThreads, kSmemBytes, stream>>>(tm, p);
   else if (poly == 9) fmha_kernel<0x100><<<grid, kThreads, kSmemBytes, stream>>>(tm, p);  // no-exp timing probe
+  else if (poly == 8) fmha_kernel<0x200><<<grid, kThreads, kSmemBytes, stream>>>(tm, p);  // no-S-load timing probe
   else fmha_kernel<0x52><<<grid, kThreads, kSmemBytes, stream>>>(tm, p);
   int rc = check_cuda(cudaGetLastError(), "fmha_kernel launch");
   if (rc == 0) count_launch();

@@ -83,9 +83,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// arrive on a barrier given by its shared::cluster address (own CTA or, via mapa, a peer CTA)
+// arrive on a barrier given by its shared::cluster address (own CTA or, via mapa, a peer CTA).
+// .relaxed: a release at cluster scope compiles to ERRBAR + a reduction and drained every pending
+// memory operation of the warp -- 13 % of all samples of the GELU GEMM (profiles/r01_summary.md).  The
+// only thing the arrive has to order is this warp's tcgen05.ld of the accumulator, which
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync already completed in program order.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // shared::cluster address of `p` (a shared::cta pointer of this CTA) inside CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t map_to_cta(const void* p, uint32_t rank) {
