@@ -32,7 +32,7 @@ constexpr int kKVStages = 2;
 constexpr uint32_t kTmemCols = 256;
 constexpr uint32_t kColS = 0, kColP = 128, kColO = 192;
 constexpr int kSoftmaxThreads = 256;  // two threads per query row (64 key columns each)
-constexpr int kThreads = kSoftmaxThreads + 32;  // + one TMA/MMA warp
+constexpr int kThreads = kSoftmaxThreads + 64;  // + Q.K^T issue warp + P.V issue warp
 constexpr int kXchgBytes = 2 * 2 * kTile * 4 + 2 * kTile * 4;  // max exchange (double buffered) + sums
 constexpr int kSmemBytes = kTileBytes * (1 + 2 * kKVStages) + 256 + kXchgBytes + 1024;
 
@@ -65,6 +65,23 @@ __device__ __forceinline__ float2 exp2_poly_x2(float2 x) {
   r.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
   return r;
 }
+
+#ifdef DOD_FMHA_TRACE
+// developer instrumentation (tools/build_variant.sh trace attention.cu -DDOD_FMHA_TRACE): SM-clock
+// stamps at the hand-off points of one CTA, read back with dod_debug_fmha_trace()
+__device__ long long g_trace[3 * 16 * 8];
+#define TRACE_ON (blockIdx.x == 3 && blockIdx.y == 5 && blockIdx.z == 20)
+#define TRACE(slot, j, pt, dep)                                                        \
+  do {                                                                                 \
+    if (TRACE_ON && lane == 0) {                                                       \
+      long long t_;                                                                    \
+      asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) : "r"(uint32_t(dep)) : "memory"); \
+      g_trace[((slot) * 16 + (j)) * 8 + (pt)] = t_;                                    \
+    }                                                                                  \
+  } while (0)
+#else
+#define TRACE(slot, j, pt, dep) do { } while (0)
+#endif
 
 struct FmhaParams {
   int seq, heads;
@@ -136,21 +153,18 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
 
   if (warp == kMmaWarp) {
     if (lane == 0) {
-      // ---------------- TMA + MMA issue (single thread) ----------------
+      // ---------------- Q/K loads + Q.K^T issue (single thread) ----------------
+      // Two issuing threads (this one and the P.V thread below) because one thread issuing all
+      // 12 MMAs of an iteration between its barrier waits took ~1750 of the ~2500 clocks an
+      // iteration lasts (tools/fmha_trace.py) and delayed S_{j+1} behind P.V_j.
       constexpr uint32_t idesc_s = make_idesc_bf16(kTile, kTile, false, false);  // Q.K^T
-      constexpr uint32_t idesc_o = make_idesc_bf16(kTile, kD, false, true);      // P.V (V MN-major)
-      const int qc = p.q_off + head * kD, kc = p.k_off + head * kD, vc = p.v_off + head * kD;
-
+      const int qc = p.q_off + head * kD, kc = p.k_off + head * kD;
       mbar_expect_tx(q_full, kTileBytes);
       tma_load_3d(sQ, &tm_qkv, q_full, qc, q_tile * kTile, b);
-      // prologue: first kKVStages K/V tiles
       for (int j = 0; j < kKVStages && j < n_kv; ++j) {
         mbar_expect_tx(&k_full[j], kTileBytes);
         tma_load_3d(sK + j * kTileBytes, &tm_qkv, &k_full[j], kc, j * kTile, b);
-        mbar_expect_tx(&v_full[j], kTileBytes);
-        tma_load_3d(sV + j * kTileBytes, &tm_qkv, &v_full[j], vc, j * kTile, b);
       }
-
       const uint64_t dq = make_sdesc_sw128(smem_u32(sQ), 16, 1024);
       auto issue_s = [&](int j) {
         const int s = j % kKVStages;
@@ -163,32 +177,38 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
         umma_commit(s_full);
         umma_commit(&k_empty[s]);
       };
-
       mbar_wait(q_full, 0);
       issue_s(0);
+      for (int j = 0; j + 1 < n_kv; ++j) {
+        const int s = j % kKVStages;
+        TRACE(2, j, 0, 0);
+        mbar_wait(s_free, j & 1);  // S_j is in registers: S columns reusable
+        TRACE(2, j, 1, 0);
+        issue_s(j + 1);
+        TRACE(2, j, 2, 0);
+        // S_j retired before s_full(j) fired, so K stage s is free: refill with K_{j+2}
+        if (j + kKVStages < n_kv) {
+          mbar_wait(&k_empty[s], (j / kKVStages) & 1);
+          mbar_expect_tx(&k_full[s], kTileBytes);
+          tma_load_3d(sK + s * kTileBytes, &tm_qkv, &k_full[s], kc, (j + kKVStages) * kTile, b);
+        }
+      }
+    }
+  } else if (warp == kMmaWarp + 1) {
+    if (lane == 0) {
+      // ---------------- V loads + P.V issue (single thread) ----------------
+      constexpr uint32_t idesc_o = make_idesc_bf16(kTile, kD, false, true);  // P.V (V MN-major)
+      const int vc = p.v_off + head * kD;
+      for (int j = 0; j < kKVStages && j < n_kv; ++j) {
+        mbar_expect_tx(&v_full[j], kTileBytes);
+        tma_load_3d(sV + j * kTileBytes, &tm_qkv, &v_full[j], vc, j * kTile, b);
+      }
       for (int j = 0; j < n_kv; ++j) {
         const int s = j % kKVStages;
-        if (j + 1 < n_kv) {
-          mbar_wait(s_free, j & 1);  // S_j is in registers: S columns reusable
-          issue_s(j + 1);
-          // S_j retired before s_full(j) fired, so K stage s is free: refill with K_{j+2}
-          if (j + kKVStages < n_kv) {
-            mbar_wait(&k_empty[s], (j / kKVStages) & 1);
-            mbar_expect_tx(&k_full[s], kTileBytes);
-            tma_load_3d(sK + s * kTileBytes, &tm_qkv, &k_full[s], kc, (j + kKVStages) * kTile, b);
-          }
-        }
         mbar_wait(&v_full[s], (j / kKVStages) & 1);
         mbar_wait(p_full, j & 1);  // P_j stored (and O rescaled if needed)
         tc_fence_after();
-        // the softmax warps saw o_full(j-1) before storing P_j, so P.V_{j-1} retired and
-        // its V stage is free: refill it with V_{j+1} (V_0, V_1 came from the prologue)
-        if (j >= 1 && j + 1 < n_kv) {
-          const int sp = (j - 1) % kKVStages;
-          mbar_wait(&v_empty[sp], ((j - 1) / kKVStages) & 1);
-          mbar_expect_tx(&v_full[sp], kTileBytes);
-          tma_load_3d(sV + sp * kTileBytes, &tm_qkv, &v_full[sp], vc, (j + 1) * kTile, b);
-        }
+        TRACE(2, j, 3, 0);
         {
           // V tile [128 keys x 64 d], d contiguous: MN-major B operand.  One MMA
           // consumes 16 keys = 16 rows of 128 B = 2 swizzle atoms (SBO 1024).
@@ -201,6 +221,14 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
         }
         umma_commit(o_full);
         umma_commit(&v_empty[s]);
+        TRACE(2, j, 4, 0);
+        // this thread is idle until P_{j+1}: wait for P.V_j to retire and refill its V stage
+        if (j + kKVStages < n_kv) {
+          mbar_wait(&v_empty[s], (j / kKVStages) & 1);
+          mbar_expect_tx(&v_full[s], kTileBytes);
+          tma_load_3d(sV + s * kTileBytes, &tm_qkv, &v_full[s], vc, (j + kKVStages) * kTile, b);
+        }
+        TRACE(2, j, 5, 0);
       }
     }
   } else {
@@ -213,8 +241,10 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
     float l = 0.0f;            // partial row sum over this thread's columns
 
     for (int j = 0; j < n_kv; ++j) {
+      TRACE(half, j, 0, 0);
       mbar_wait(s_full, j & 1);
       tc_fence_after();
+      TRACE(half, j, 1, 0);
       const int valid = p.seq - j * kTile - half * 64;  // keys valid in this thread's 64 columns
       // kPolyMask == 0 (default): S is read from TMEM once and held in 64 registers.  The polynomial
       // variants need more live registers than the 96 available with 2 CTAs/SM, so they read S twice
@@ -269,8 +299,10 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
       }
       // row maximum over both halves: exchange through shared memory (double buffered by parity)
       float* xm = xmax + (j & 1) * 2 * kTile;
+      TRACE(half, j, 2, __float_as_uint(fmaxf(mx0, mx1)));
       xm[half * kTile + row] = fmaxf(mx0, mx1);
       pair_sync(quad);
+      TRACE(half, j, 3, 0);
       const float mx = fmaxf(fmaxf(mx0, mx1), xm[(half ^ 1) * kTile + row]);
       const float m_new = fmaxf(m_used, mx * p.scale_log2);
       // lazy max: keep the stale max while it is within 2^8 of the true one
@@ -315,10 +347,12 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
         }
       }
       l = l * alpha + (sum2.x + sum2.y);
+      TRACE(half, j, 4, pk[31] ^ pk[15] ^ __float_as_uint(l));
 
       if (j > 0) {
         mbar_wait(o_full, (j - 1) & 1);  // P.V of the previous tile retired
         tc_fence_after();
+        TRACE(half, j, 5, 0);
         if (__any_sync(0xffffffffu, bump)) {
           // rescale this thread's half of the running O row (rare after the first tiles)
           uint32_t o[32];
@@ -334,6 +368,7 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
+      TRACE(half, j, 6, 0);
     }
 
     // ---- epilogue: O / l -> ctx ----
@@ -370,6 +405,12 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
 
 }  // namespace
 }  // namespace dod
+
+#ifdef DOD_FMHA_TRACE
+extern "C" DOD_API int32_t dod_debug_fmha_trace(long long* host) {
+  return int32_t(cudaMemcpyFromSymbol(host, dod::g_trace, sizeof(long long) * 3 * 16 * 8));
+}
+#endif
 
 extern "C" int32_t dod_fmha_fwd(const dod_fmha_args* a, dod_stream_t stream_) {
   using namespace dod;
