@@ -56,7 +56,13 @@ struct GemmParams {
   int out_f32;
   int patch_rows;
   int direct;  // 1: register -> global epilogue (patch rows / shapes TMA cannot store)
+  int a_trans, w_trans;  // operand stored [K, M] / [K, N]: MN-major smem tiles (64-column blocks 8 KB apart)
 };
+
+// MN-major operand tile in shared memory: [MN / 64 blocks][64 K rows][64 MN elements = 128 B],
+// 128B-swizzled; one TMA box per block.  tcgen05 descriptor: LBO = 8192 (between 64-wide MN blocks),
+// SBO = 1024 (between 8-row K groups); a 16-deep K step advances the start address by 16 * 128 B.
+constexpr int kMnBlockBytes = 64 * BK * 2;
 
 // two batch levels (outer x inner) of a problem; a level that is not used still needs a valid
 // (16-byte multiple, non-zero) TMA stride
@@ -429,8 +435,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
           uint8_t* sb = sa + L::kStageA;
           mbar_expect_tx(&full[s], L::kStage);
           if (kb < p.K1blocks) {
-            tma_load_4d(sa, &tm_a, &full[s], kb * BK, mb * BM, bz % p.batch_inner, bz / p.batch_inner);
-            tma_load_4d(sb, &tm_w, &full[s], kb * BK, nb * BN, bz % p.batch_inner, bz / p.batch_inner);
+            const int bi = bz % p.batch_inner, bo = bz / p.batch_inner;
+            if (p.a_trans) {
+#pragma unroll
+              for (int i = 0; i < BM / 64; ++i)
+                tma_load_4d(sa + i * kMnBlockBytes, &tm_a, &full[s], mb * BM + i * 64, kb * BK, bi, bo);
+            } else {
+              tma_load_4d(sa, &tm_a, &full[s], kb * BK, mb * BM, bi, bo);
+            }
+            if (p.w_trans) {
+#pragma unroll
+              for (int i = 0; i < BN / 64; ++i)
+                tma_load_4d(sb + i * kMnBlockBytes, &tm_w, &full[s], nb * BN + i * 64, kb * BK, bi, bo);
+            } else {
+              tma_load_4d(sb, &tm_w, &full[s], kb * BK, nb * BN, bi, bo);
+            }
           } else {
             tma_load_2d(sa, &tm_a2, &full[s], (kb - p.K1blocks) * BK, mb * BM);
             tma_load_2d(sb, &tm_w2, &full[s], (kb - p.K1blocks) * BK, nb * BN);
@@ -442,7 +461,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, false, false);
+      const uint32_t idesc = make_idesc_bf16(BM, BN, p.a_trans != 0, p.w_trans != 0);
+      const uint32_t a_lbo = p.a_trans ? kMnBlockBytes : 16, b_lbo = p.w_trans ? kMnBlockBytes : 16;
+      // descriptor start-address step (in 16-byte units) of one 16-deep K slice
+      const uint64_t a_step = p.a_trans ? 16 * 128 / 16 : 2, b_step = p.w_trans ? 16 * 128 / 16 : 2;
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -457,13 +479,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + s * L::kStage);
           const uint32_t sb = sa + L::kStageA;
-          const uint64_t da = make_sdesc_sw128(sa, 16, 1024);
-          const uint64_t db = make_sdesc_sw128(sb, 16, 1024);
+          const uint64_t da = make_sdesc_sw128(sa, a_lbo, 1024);
+          const uint64_t db = make_sdesc_sw128(sb, b_lbo, 1024);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 bf16 = 32 B inside the 128-B swizzle row: +2 in (addr >> 4)
-            umma_ss(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc,
-                    (kb | k) != 0 ? 1u : 0u);
+            // K-major: advance 16 bf16 = 32 B inside the 128-B swizzle row: +2 in (addr >> 4)
+            umma_ss(d_tmem, da + a_step * k, db + b_step * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty[s]);  // frees the smem stage when these MMAs retire
           if (kb == kblocks - 1) umma_commit(&tfull[acc]);
@@ -614,8 +635,19 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
           const uint32_t full_leader = map_to_cta(&full[s], 0);
           if (rank == 0) mbar_expect_tx(&full[s], 2 * L::kStage);  // bytes of both CTAs
           if (kb < p.K1blocks) {
-            tma_load_4d_2sm(sa, &tm_a, full_leader, kb * BK, row_a, bz % p.batch_inner, bz / p.batch_inner);
-            tma_load_4d_2sm(sb, &tm_w, full_leader, kb * BK, row_w, bz % p.batch_inner, bz / p.batch_inner);
+            const int bi = bz % p.batch_inner, bo = bz / p.batch_inner;
+            if (p.a_trans) {
+              tma_load_4d_2sm(sa, &tm_a, full_leader, row_a, kb * BK, bi, bo);
+              tma_load_4d_2sm(sa + kMnBlockBytes, &tm_a, full_leader, row_a + 64, kb * BK, bi, bo);
+            } else {
+              tma_load_4d_2sm(sa, &tm_a, full_leader, kb * BK, row_a, bi, bo);
+            }
+            if (p.w_trans) {
+              tma_load_4d_2sm(sb, &tm_w, full_leader, row_w, kb * BK, bi, bo);
+              tma_load_4d_2sm(sb + kMnBlockBytes, &tm_w, full_leader, row_w + 64, kb * BK, bi, bo);
+            } else {
+              tma_load_4d_2sm(sb, &tm_w, full_leader, kb * BK, row_w, bi, bo);
+            }
           } else {
             tma_load_3d_2sm(sa, &tm_a2, full_leader, (kb - p.K1blocks) * BK, row_a, 0);
             tma_load_3d_2sm(sb, &tm_w2, full_leader, (kb - p.K1blocks) * BK, row_w, 0);
@@ -627,7 +659,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(256, BN, false, false);
+      const uint32_t idesc = make_idesc_bf16(256, BN, p.a_trans != 0, p.w_trans != 0);
+      const uint32_t a_lbo = p.a_trans ? kMnBlockBytes : 16, b_lbo = p.w_trans ? kMnBlockBytes : 16;
+      const uint64_t a_step = p.a_trans ? 16 * 128 / 16 : 2, b_step = p.w_trans ? 16 * 128 / 16 : 2;
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -642,11 +676,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + s * L::kStage);
           const uint32_t sb = sa + L::kStageA;
-          const uint64_t da = make_sdesc_sw128(sa, 16, 1024);
-          const uint64_t db = make_sdesc_sw128(sb, 16, 1024);
+          const uint64_t da = make_sdesc_sw128(sa, a_lbo, 1024);
+          const uint64_t db = make_sdesc_sw128(sb, b_lbo, 1024);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            umma_ss_2sm(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_ss_2sm(d_tmem, da + a_step * k, db + b_step * k, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit_2sm(&empty[s], 3);  // frees the stage in BOTH CTAs
           if (kb == kblocks - 1) umma_commit_2sm(&tfull[acc], 3);
           if (++s == kStages) { s = 0; ph ^= 1; }
@@ -703,8 +737,12 @@ int launch2(const dod_gemm_args& a, cudaStream_t stream) {
   }
   CUtensorMap tm_a, tm_w, tm_a2, tm_w2, tm_out, tm_res;
   const BatchDims bd(a);
-  if (int rc = make_tmap_4d(&tm_a, a.a, 2, bd.outer, bd.inner, a.m, a.k, bd.os_a, bd.is_a, a.lda, 128, BK, 128)) return rc;
-  if (int rc = make_tmap_4d(&tm_w, a.w, 2, bd.outer, bd.inner, a.n, a.k, bd.os_w, bd.is_w, a.ldw, 128, BK, 128)) return rc;
+  if (int rc = a.a_trans ? make_tmap_4d(&tm_a, a.a, 2, bd.outer, bd.inner, a.k, a.m, bd.os_a, bd.is_a, a.lda, BK, 64, 128)
+                         : make_tmap_4d(&tm_a, a.a, 2, bd.outer, bd.inner, a.m, a.k, bd.os_a, bd.is_a, a.lda, 128, BK, 128))
+    return rc;
+  if (int rc = a.w_trans ? make_tmap_4d(&tm_w, a.w, 2, bd.outer, bd.inner, a.k, a.n, bd.os_w, bd.is_w, a.ldw, BK, 64, 128)
+                         : make_tmap_4d(&tm_w, a.w, 2, bd.outer, bd.inner, a.n, a.k, bd.os_w, bd.is_w, a.ldw, 128, BK, 128))
+    return rc;
   if (a.a2) {
     if (int rc = make_tmap_3d(&tm_a2, a.a2, 2, 1, a.m, a.k2, uint64_t(a.m) * a.lda2, a.lda2, 128, BK, 128)) return rc;
     if (int rc = make_tmap_3d(&tm_w2, a.w2, 2, 1, a.n, a.k2, uint64_t(a.n) * a.ldw2, a.ldw2, 128, BK, 128)) return rc;
@@ -741,6 +779,8 @@ int launch2(const dod_gemm_args& a, cudaStream_t stream) {
   p.out_f32 = out_f32;
   p.patch_rows = 0;
   p.direct = 0;
+  p.a_trans = a.a_trans;
+  p.w_trans = a.w_trans;
   const int tiles = p.tiles_m * p.tiles_n * p.batch;
   const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
   gemm2_kernel<RES><<<2 * pairs, kThreads, L::kTotal, stream>>>(tm_a, tm_w, tm_a2, tm_w2, tm_out, tm_res, p);
@@ -758,8 +798,12 @@ int launch(const dod_gemm_args& a, cudaStream_t stream, bool direct) {
   }
   CUtensorMap tm_a, tm_w, tm_a2, tm_w2, tm_out, tm_res;
   const BatchDims bd(a);
-  if (int rc = make_tmap_4d(&tm_a, a.a, 2, bd.outer, bd.inner, a.m, a.k, bd.os_a, bd.is_a, a.lda, BM, BK, 128)) return rc;
-  if (int rc = make_tmap_4d(&tm_w, a.w, 2, bd.outer, bd.inner, a.n, a.k, bd.os_w, bd.is_w, a.ldw, BN, BK, 128)) return rc;
+  if (int rc = a.a_trans ? make_tmap_4d(&tm_a, a.a, 2, bd.outer, bd.inner, a.k, a.m, bd.os_a, bd.is_a, a.lda, BK, 64, 128)
+                         : make_tmap_4d(&tm_a, a.a, 2, bd.outer, bd.inner, a.m, a.k, bd.os_a, bd.is_a, a.lda, BM, BK, 128))
+    return rc;
+  if (int rc = a.w_trans ? make_tmap_4d(&tm_w, a.w, 2, bd.outer, bd.inner, a.k, a.n, bd.os_w, bd.is_w, a.ldw, BK, 64, 128)
+                         : make_tmap_4d(&tm_w, a.w, 2, bd.outer, bd.inner, a.n, a.k, bd.os_w, bd.is_w, a.ldw, BN, BK, 128))
+    return rc;
   if (a.a2) {
     if (int rc = make_tmap_2d(&tm_a2, a.a2, 2, a.m, a.k2, a.lda2, BM, BK)) return rc;
     if (int rc = make_tmap_2d(&tm_w2, a.w2, 2, a.n, a.k2, a.ldw2, BN, BK)) return rc;
@@ -800,6 +844,8 @@ int launch(const dod_gemm_args& a, cudaStream_t stream, bool direct) {
   p.out_f32 = out_f32;
   p.patch_rows = a.patch_rows;
   p.direct = direct;
+  p.a_trans = a.a_trans;
+  p.w_trans = a.w_trans;
   const int tiles = p.tiles_m * p.tiles_n * p.batch;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   gemm_kernel<BN, RES><<<grid, kThreads, L::kTotal, stream>>>(tm_a, tm_w, tm_a2, tm_w2, tm_out, tm_res, p);
@@ -840,8 +886,12 @@ extern "C" int32_t dod_gemm_bf16(const dod_gemm_args* a, dod_stream_t stream_) {
               (long long)a->m, (long long)a->n, (long long)a->k);
   DOD_REQUIRE(a->m < (1ll << 31) && a->n < (1ll << 31) && a->k < (1ll << 31),
               "dod_gemm_bf16: dimension too large");
-  DOD_REQUIRE(a->lda % 8 == 0 && a->ldw % 8 == 0 && a->lda >= a->k && a->ldw >= a->k,
-              "dod_gemm_bf16: lda/ldw must be >= k and multiples of 8 (16-byte TMA strides)");
+  DOD_REQUIRE(a->lda % 8 == 0 && a->ldw % 8 == 0 && a->lda >= (a->a_trans ? a->m : a->k) &&
+                  a->ldw >= (a->w_trans ? a->n : a->k),
+              "dod_gemm_bf16: lda/ldw must cover the stored row (k, or m / n for transposed views) and be "
+              "multiples of 8 (16-byte TMA strides)");
+  DOD_REQUIRE(!(a->a_trans || a->w_trans) || (!a->a2 && !a->w2),
+              "dod_gemm_bf16: transposed operand views take no second K segment");
   DOD_REQUIRE((uintptr_t(a->a) & 15) == 0 && (uintptr_t(a->w) & 15) == 0 &&
                   (uintptr_t(a->out) & 15) == 0,
               "dod_gemm_bf16: a/w/out must be 16-byte aligned");

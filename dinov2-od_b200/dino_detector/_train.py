@@ -66,7 +66,6 @@ class TLinear:
         n, k = weight.shape
         self.n, self.k, self.n_pad = n, k, _pad8(n)
         self.w = ops.cast_pad_bf16(weight.detach().float().contiguous(), _pad8(k), dst_rows=self.n_pad)
-        self.wT = ops.transpose(self.w)                       # [k_pad, n_pad]
         self.bias = None
         if bias is not None:
             self.bias = torch.zeros(self.n_pad, dtype=F32, device=weight.device)
@@ -79,12 +78,13 @@ class TLinear:
         """dy bf16 [M, n_pad] (zero in padded columns), x bf16 [M, k] -> dx bf16 [M, k_pad]."""
         dev = dy.device
         gw = grads.buf(("w", id(self.weight)), (self.n_pad, self.w.shape[1]), dev)
-        ops.gemm(ops.transpose(dy), ops.transpose(x), None, residual=gw, out=gw)        # dW += dy^T x
+        # dW += dy^T x: both operands are read as stored ([M, n] / [M, k], the reduction dim M outermost)
+        ops.gemm(dy, x, None, residual=gw, out=gw, a_trans=True, w_trans=True)
         if self.bias_p is not None:
             ops.colsum(dy, grads.buf(("b", id(self.bias_p)), (self.n_pad,), dev))
         if not need_dx:
             return None
-        return ops.gemm(dy, self.wT[:, :self.n_pad], None)                              # dx = dy W
+        return ops.gemm(dy, self.w, None, w_trans=True)                                 # dx = dy W
 
     def collect(self, grads, out):
         gw = grads.bufs.get(("w", id(self.weight)))
@@ -178,7 +178,7 @@ def attention_fwd_dropout(q3, k3, v3, heads, dh, scale, drop_p, seed):
     s_full = torch.empty((b, heads, lq, lkp), dtype=F32, device=q3.device)
     ops.gemm_batched(q4, k4, s_full[..., :lk])
     pd = ops.softmax_rows(s_full.view(-1, lkp), lk, scale, ldp=lkp, drop_p=drop_p, seed=seed)
-    ops.gemm_batched(pd.view(b, heads, lq, lkp)[..., :lk], ops.transpose(v4), _heads(ctx, heads, dh))
+    ops.gemm_batched(pd.view(b, heads, lq, lkp)[..., :lk], v4, _heads(ctx, heads, dh), w_trans=True)
     return ctx
 
 
@@ -201,9 +201,10 @@ def attention_bwd(q3, k3, v3, dctx3, dq3, dk3, dv3, heads, dh, scale, drop_p=0.0
     ds = ops.softmax_bwd_rows(p, s2d, lk, scale, drop_p=drop_p, seed=seed)           # dS
     ds4 = ds.view(b, heads, lq, lkp)[..., :lk]
     pd4 = pd.view(b, heads, lq, lkp)[..., :lk]
-    ops.gemm_batched(ds4, ops.transpose(k4), _heads(dq3, heads, dh))                 # dQ = dS K
-    ops.gemm_batched(ops.transpose(ds4), ops.transpose(q4), _heads(dk3, heads, dh))  # dK = dS^T Q
-    ops.gemm_batched(ops.transpose(pd4), ops.transpose(do4), _heads(dv3, heads, dh))  # dV = dropout(P)^T dO
+    # the transposed products read dS / P / K / Q / dO as stored (MN-major tcgen05 operands)
+    ops.gemm_batched(ds4, k4, _heads(dq3, heads, dh), w_trans=True)                  # dQ = dS K
+    ops.gemm_batched(ds4, q4, _heads(dk3, heads, dh), a_trans=True, w_trans=True)    # dK = dS^T Q
+    ops.gemm_batched(pd4, do4, _heads(dv3, heads, dh), a_trans=True, w_trans=True)   # dV = dropout(P)^T dO
 
 
 # ---------------------------------------------------------------------------
@@ -305,7 +306,6 @@ class _FusedLinear(TLinear):
         self.weight, self.bias_p, self.name = w, bias, name       # identity keys for the grad buffers
         self.n, self.k, self.n_pad = n, k, _pad8(n)
         self.w = ops.cast_pad_bf16(w, _pad8(k), dst_rows=self.n_pad)
-        self.wT = ops.transpose(self.w)
         self.bias = torch.zeros(self.n_pad, dtype=F32, device=w.device)
         self.bias[:n].copy_(bias)
 

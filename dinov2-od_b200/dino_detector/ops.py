@@ -66,13 +66,15 @@ def _rowmajor(t: torch.Tensor, name: str):
 
 
 def gemm(a, w, bias=None, *, act=ACT_NONE, scale=None, residual=None, out=None,
-         out_dtype=torch.bfloat16, a2=None, w2=None, patch_rows=0, out_rows=None):
-    """out = residual + scale * act(a @ w.T (+ a2 @ w2.T) + bias); a, w (a2, w2) bf16."""
+         out_dtype=torch.bfloat16, a2=None, w2=None, patch_rows=0, out_rows=None, a_trans=False, w_trans=False):
+    """out = residual + scale * act(a @ w.T (+ a2 @ w2.T) + bias); a, w (a2, w2) bf16.
+    a_trans: `a` is the stored transpose [K, M] (out = a.T @ ...); w_trans: `w` is stored [K, N]
+    (out = ... @ w) -- the kernel reads them as MN-major operands, no transposed copy is made."""
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
     lda, ldw = _rowmajor(a, "a"), _rowmajor(w, "w")
-    m, k = a.shape
-    n = w.shape[0]
-    assert w.shape[1] == k, (a.shape, w.shape)
+    k, m = (a.shape if a_trans else a.shape[::-1])
+    k_w, n = (w.shape if w_trans else w.shape[::-1])
+    assert k_w == k, (a.shape, w.shape, a_trans, w_trans)
     n_out = n // 2 if act == ACT_SWIGLU else n
     if out is None:
         out = torch.empty((out_rows if out_rows is not None else m, n_out), dtype=out_dtype,
@@ -80,7 +82,8 @@ def gemm(a, w, bias=None, *, act=ACT_NONE, scale=None, residual=None, out=None,
     ldo = _rowmajor(out, "out")
     kw = dict(a=a, w=w, m=m, n=n, k=k, lda=lda, ldw=ldw, bias=bias, act=act, scale=scale,
               residual=residual, ldr=_rowmajor(residual, "residual") if residual is not None else 0,
-              out=out, ldo=ldo, out_dtype=_DT[out.dtype], patch_rows=patch_rows)
+              out=out, ldo=ldo, out_dtype=_DT[out.dtype], patch_rows=patch_rows,
+              a_trans=int(a_trans), w_trans=int(w_trans))
     if a2 is not None:
         assert a2.dtype == torch.bfloat16 and w2.dtype == torch.bfloat16
         assert a2.shape[0] == m and w2.shape[0] == n and a2.shape[1] == w2.shape[1]
@@ -266,26 +269,29 @@ ELT_CAST, ELT_SCALE_COLS, ELT_ADD, ELT_GELU_FWD, ELT_GELU_BWD, ELT_RELU_BWD, ELT
     ELT_SWIGLU_FWD, ELT_SWIGLU_BWD, ELT_DROPOUT, ELT_AXPBY = range(11)
 
 
-def gemm_batched(a, w, out, *, bias=None, act=ACT_NONE):
+def gemm_batched(a, w, out, *, bias=None, act=ACT_NONE, a_trans=False, w_trans=False):
     """out[..] = act(a[..] @ w[..].T + bias) over one or two leading batch dims:
     a [B, M, K] / [B, H, M, K], w [B, N, K] / [B, H, N, K], out [B, M, N] / [B, H, M, N]; strided views
     with unit inner stride and row / batch strides that are multiples of 8 elements (e.g. head slices
-    of a fused qkv buffer viewed as [B, H, L, dh])."""
+    of a fused qkv buffer viewed as [B, H, L, dh]).  a_trans / w_trans: the operand is given as its
+    stored transpose ([.., K, M] / [.., K, N]) and read MN-major by the kernel."""
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
     assert a.dim() == w.dim() == out.dim() and a.dim() in (3, 4)
     assert a.stride(-1) == 1 and w.stride(-1) == 1 and out.stride(-1) == 1
     if a.dim() == 3:
         a, w, out = a.unsqueeze(1), w.unsqueeze(1), out.unsqueeze(1)
-    nb, nh, m, k = a.shape
-    n = w.shape[2]
-    assert tuple(w.shape) == (nb, nh, n, k) and tuple(out.shape) == (nb, nh, m, n), (a.shape, w.shape, out.shape)
+    nb, nh = a.shape[:2]
+    k, m = (a.shape[2:] if a_trans else a.shape[:1:-1])
+    k_w, n = (w.shape[2:] if w_trans else w.shape[:1:-1])
+    assert k_w == k and tuple(w.shape[:2]) == (nb, nh) and tuple(out.shape) == (nb, nh, m, n), \
+        (a.shape, w.shape, out.shape, a_trans, w_trans)
     with _Timed("gemm", 2.0 * nb * nh * m * n * k):
         _dod.call("dod_gemm_bf16", _stream(a), a=a, w=w, m=m, n=n, k=k, lda=a.stride(2), ldw=w.stride(2),
                   bias=bias, act=act, out=out, ldo=out.stride(2), out_dtype=_DT[out.dtype], batch=nb,
                   batch_stride_a=a.stride(0) if nb > 1 else 0, batch_stride_w=w.stride(0) if nb > 1 else 0,
                   batch_stride_out=out.stride(0) if nb > 1 else 0, batch_inner=nh,
                   inner_stride_a=a.stride(1) if nh > 1 else 0, inner_stride_w=w.stride(1) if nh > 1 else 0,
-                  inner_stride_out=out.stride(1) if nh > 1 else 0)
+                  inner_stride_out=out.stride(1) if nh > 1 else 0, a_trans=int(a_trans), w_trans=int(w_trans))
     return out
 
 

@@ -92,6 +92,12 @@ typedef struct {
    * batch * batch_inner problems; problem (bo, bi) starts at bo * batch_stride_* + bi * inner_stride_*.
    * Strides are in elements and multiples of 8 (16 bytes); 0 / 1 = no inner level.                    */
   int64_t batch_inner, inner_stride_a, inner_stride_w, inner_stride_out;
+  /* transposed operand views (the backward pass: dW = dY^T X, dX = dY W, dK = dS^T Q, ... without
+   * materialising a transpose).  a_trans != 0: `a` holds A^T, i.e. [K, M] row-major with row stride
+   * lda >= M (A[m, k] = a[k * lda + m]).  w_trans != 0: `w` holds W^T, [K, N] row-major with row
+   * stride ldw >= N.  The tiles are then fed to tcgen05.mma as MN-major operands.  Not combined with
+   * the second K segment (a2 / w2).                                                                 */
+  int32_t a_trans, w_trans;
 } dod_gemm_args;
 DOD_API int32_t dod_gemm_bf16(const dod_gemm_args* a, dod_stream_t stream);
 

@@ -70,6 +70,52 @@ def test_gemm_batched_two_levels(ops):
     assert _rel(d4, p.float() @ k4.float()) < 1e-2
 
 
+@pytest.mark.parametrize("m,n,k", [(200, 64, 333), (136, 120, 64), (1370, 64, 1370), (640, 768, 1000),
+                                   (1024, 1024, 4384), (520, 264, 72)])
+@pytest.mark.parametrize("a_trans,w_trans", [(True, False), (False, True), (True, True)])
+def test_gemm_transposed_views(ops, m, n, k, a_trans, w_trans):
+    """a_trans / w_trans read the stored transposes as MN-major tcgen05 operands (dW = dY^T X,
+    dX = dY W without a transposed copy); both the 1-CTA and the CTA-pair kernel."""
+    g = _g(m + n + k)
+    pad = lambda v: (v + 7) // 8 * 8
+    a = _randn((k, pad(m)) if a_trans else (m, pad(k)), g).bfloat16()
+    w = _randn((k, pad(n)) if w_trans else (n, pad(k)), g).bfloat16()
+    a_v = a[:, :m] if a_trans else a[:, :k]
+    w_v = w[:, :n] if w_trans else w[:, :k]
+    out = torch.empty((m, pad(n)), dtype=torch.float32, device="cuda")[:, :n]
+    ops.gemm(a_v, w_v, None, out=out, a_trans=a_trans, w_trans=w_trans)
+    af = a_v.float().t() if a_trans else a_v.float()
+    wf = w_v.float() if w_trans else w_v.float().t()
+    assert _rel(out, af @ wf) < 2e-5
+    # accumulate into an fp32 buffer through the residual path (weight-gradient use)
+    if n % 8 == 0:
+        acc = _randn((m, n), g)
+        want = acc + af @ wf
+        ops.gemm(a_v, w_v, None, residual=acc, out=acc, a_trans=a_trans, w_trans=w_trans)
+        assert _rel(acc, want) < 2e-5
+
+
+def test_gemm_batched_transposed_views(ops):
+    """dK = dS^T Q and dQ = dS K over (image, head) batches without transposed copies."""
+    g = _g(11)
+    b, h, lq, lk = 2, 3, 300, 257
+    d = h * 64
+    lkp = (lk + 7) // 8 * 8
+    ds_full = torch.zeros((b, h, lq, lkp), dtype=torch.bfloat16, device="cuda")
+    ds_full[..., :lk] = _randn((b, h, lq, lk), g).bfloat16()
+    ds = ds_full[..., :lk]
+    q3 = _randn((b, lq, d), g).bfloat16()
+    k3 = _randn((b, lk, d), g).bfloat16()
+    heads = lambda x3, l: x3.as_strided((b, h, l, 64), (l * d, 64, d, 1), 0)
+    q4, k4 = heads(q3, lq), heads(k3, lk)
+    dk3 = torch.zeros((b, lk, d), dtype=torch.bfloat16, device="cuda")
+    ops.gemm_batched(ds, q4, heads(dk3, lk), a_trans=True, w_trans=True)      # dK = dS^T Q
+    assert _rel(heads(dk3, lk), ds.float().transpose(-1, -2) @ q4.float()) < 1e-2
+    dq3 = torch.zeros((b, lq, d), dtype=torch.bfloat16, device="cuda")
+    ops.gemm_batched(ds, k4, heads(dq3, lq), w_trans=True)                    # dQ = dS K
+    assert _rel(heads(dq3, lq), ds.float() @ k4.float()) < 1e-2
+
+
 def test_transpose(ops):
     g = _g(1)
     x = _randn((3, 257, 100), g).bfloat16()
