@@ -89,6 +89,7 @@ struct FmhaParams {
   float scale_log2;  // scale * log2(e)
   __nv_bfloat16* ctx;
   int64_t ldo;
+  float* lse;  // optional [B, heads, S]
 };
 
 __device__ __forceinline__ void pair_sync(int quad) {
@@ -374,10 +375,15 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
     // ---- epilogue: O / l -> ctx ----
     xsum[half * kTile + row] = l;
     pair_sync(quad);
-    const float inv_l = 1.0f / (l + xsum[(half ^ 1) * kTile + row]);
+    const float l_row = l + xsum[(half ^ 1) * kTile + row];
+    const float inv_l = 1.0f / l_row;
     mbar_wait(o_full, (n_kv - 1) & 1);
     tc_fence_after();
     const int q_row = q_tile * kTile + row;
+    // log-sum-exp of the scaled scores in the log2 domain (m_used is the possibly stale maximum the
+    // probabilities were formed against, so m_used + log2(sum) is exact): saved for dod_fmha_bwd
+    if (p.lse != nullptr && half == 0 && q_row < p.seq)
+      p.lse[(int64_t(b) * p.heads + head) * p.seq + q_row] = m_used + log2f(l_row);
     __nv_bfloat16* dst = p.ctx + (int64_t(b) * p.seq + q_row) * p.ldo + head * kD + half * 32;
     uint32_t o[32];
     tmem_ld_32x32(t_lane + kColO + half * 32, o);
@@ -450,6 +456,7 @@ extern "C" int32_t dod_fmha_fwd(const dod_fmha_args* a, dod_stream_t stream_) {
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.ctx = reinterpret_cast<__nv_bfloat16*>(a->ctx);
   p.ldo = a->ldo;
+  p.lse = a->lse;
   dim3 grid((a->seq + kTile - 1) / kTile, a->heads, a->batch);
   if (poly == 0) fmha_kernel<0x00><<<grid, kThreads, kSmemBytes, stream>>>(tm, p);
   else if (poly == 2) fmha_kernel<0x12><<<grid, kThreads, kSmemBytes, stream>>>(tm, p);

@@ -231,7 +231,8 @@ class EncTrainLayer:
         sv = {"x": x}
         sv["h1"] = ops.layernorm(x, *self.n1, 1e-6)
         sv["qkv"], sv["t1"] = self.qkv.fwd(sv["h1"])
-        sv["ctx"] = ops.fmha(sv["qkv"], b, n, heads, q_off=0, k_off=d, v_off=2 * d, scale=0.125)
+        sv["lse"] = torch.empty((b, heads, n), dtype=F32, device=x.device)
+        sv["ctx"] = ops.fmha(sv["qkv"], b, n, heads, q_off=0, k_off=d, v_off=2 * d, scale=0.125, lse=sv["lse"])
         sv["x_mid"], sv["t2"] = self.proj.fwd(sv["ctx"], scale=self.ls1, residual=x, out_dtype=F32)
         sv["h2"] = ops.layernorm(sv["x_mid"], *self.n2, 1e-6)
         sv["z"], sv["t3"] = self.fc1.fwd(sv["h2"])
@@ -254,11 +255,10 @@ class EncTrainLayer:
         dx_mid = ops.layernorm_bwd(dh2, sv["x_mid"], self.n2[0], 1e-6, dres=dx_out)
         dy = ops.eltwise(ops.ELT_SCALE_COLS, dx_mid, vec=self.ls1, out_dtype=BF16)
         dctx = self.proj.bwd(dy, sv["ctx"], sv["t2"], grads)
-        qkv3 = sv["qkv"].view(b, n, 3 * d)
         dqkv = torch.empty_like(sv["qkv"])
-        dq3 = dqkv.view(b, n, 3 * d)
-        attention_bwd(qkv3[:, :, :d], qkv3[:, :, d:2 * d], qkv3[:, :, 2 * d:], dctx.view(b, n, d),
-                      dq3[:, :, :d], dq3[:, :, d:2 * d], dq3[:, :, 2 * d:], heads, 64, 0.125)
+        # fused flash-style backward: probabilities recomputed from q, k and the saved log-sum-exp
+        ops.fmha_bwd(sv["qkv"], sv["ctx"], dctx, sv["lse"], dqkv, b, n, heads, q_off=0, k_off=d, v_off=2 * d,
+                     scale=0.125)
         dh1 = self.qkv.bwd(dqkv, sv["h1"], sv["t1"], grads, need_dx=need_dx_in)
         if not need_dx_in:
             return None

@@ -150,17 +150,37 @@ def pos_resize_bicubic(pos, g0, gh, gw):
     return out
 
 
-def fmha(qkv, batch, seq, heads, *, q_off, k_off, v_off, scale, out=None):
-    """Self-attention over a fused projection buffer qkv [B*S, ld] (bf16), head dim 64."""
+def fmha(qkv, batch, seq, heads, *, q_off, k_off, v_off, scale, out=None, lse=None):
+    """Self-attention over a fused projection buffer qkv [B*S, ld] (bf16), head dim 64.
+    lse: optional f32 [batch, heads, seq] that receives the per-row log-sum-exp (for fmha_bwd)."""
     assert qkv.dtype == torch.bfloat16
     ld = _rowmajor(qkv, "qkv")
     assert qkv.shape[0] == batch * seq
     if out is None:
         out = torch.empty((batch * seq, heads * 64), dtype=torch.bfloat16, device=qkv.device)
+    if lse is not None:
+        assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == batch * heads * seq
     with _Timed("fmha", 4.0 * batch * heads * seq * seq * 64):
         _dod.call("dod_fmha_fwd", _stream(qkv), qkv=qkv, ctx=out, batch=batch, seq=seq, heads=heads,
-                  ld=ld, ldo=_rowmajor(out, "out"), q_off=q_off, k_off=k_off, v_off=v_off, scale=scale)
+                  ld=ld, ldo=_rowmajor(out, "out"), q_off=q_off, k_off=k_off, v_off=v_off, scale=scale, lse=lse)
     return out
+
+
+def fmha_bwd(qkv, ctx, dctx, lse, dqkv, batch, seq, heads, *, q_off, k_off, v_off, scale):
+    """Backward of fmha(): writes bf16 dQ / dK / dV into the head slices of dqkv [B*S, ld] at the same
+    column offsets as q / k / v in qkv.  ctx is the forward output, lse the forward's log-sum-exp."""
+    assert qkv.dtype == ctx.dtype == dctx.dtype == dqkv.dtype == torch.bfloat16
+    assert lse.dtype == torch.float32 and lse.is_contiguous() and lse.numel() == batch * heads * seq
+    hd = heads * 64
+    dsum = torch.empty_like(lse)
+    dq_acc = torch.zeros((batch * seq, hd), dtype=torch.float32, device=qkv.device)
+    with _Timed("fmha_bwd", 10.0 * batch * heads * seq * seq * 64):
+        _dod.call("dod_fmha_bwd", _stream(qkv), qkv=qkv, ctx=ctx, dctx=dctx, lse=lse, dsum=dsum, dq_acc=dq_acc,
+                  dqkv=dqkv, batch=batch, seq=seq, heads=heads, ld=_rowmajor(qkv, "qkv"), ldo=_rowmajor(ctx, "ctx"),
+                  lddo=_rowmajor(dctx, "dctx"), ld_dq=hd, ld_dqkv=_rowmajor(dqkv, "dqkv"), q_off=q_off, k_off=k_off,
+                  v_off=v_off, scale=scale)
+    eltwise(ELT_CAST, dq_acc, out=dqkv[:, q_off:q_off + hd])
+    return dqkv
 
 
 def mha_small(q, k, v, batch, lq, lk, heads, head_dim, scale, out=None):

@@ -154,8 +154,29 @@ typedef struct {
   int64_t batch, seq, heads, ld, ldo;
   int64_t q_off, k_off, v_off; /* column offsets (elements)                    */
   float scale;     /* 1/sqrt(64)                                              */
+  float* lse;      /* optional f32 [B, heads, S]: log2-domain log-sum-exp of the scaled
+                      scores of every query row (saved for dod_fmha_bwd), or NULL */
 } dod_fmha_args;
 DOD_API int32_t dod_fmha_fwd(const dod_fmha_args* a, dod_stream_t stream);
+
+/* fused backward of dod_fmha_fwd (autograd of SDPA, modeling_dinov2.py:215-229, reached from
+ * loss.backward() at train.py:1101 for the LoRA-wrapped encoder layers).  Probabilities are
+ * recomputed from q, k and `lse`; nothing of size [S, S] is written to memory.
+ * dK and dV are written (bf16) into dqkv at k_off / v_off; dQ is ACCUMULATED (fp32, TMA
+ * reduce-add over the key tiles) into dq_acc, which the caller zero-fills and converts.   */
+typedef struct {
+  const void* qkv;   /* bf16 [B*S, ld]    forward input                                */
+  const void* ctx;   /* bf16 [B*S, ldo]   forward output O                             */
+  const void* dctx;  /* bf16 [B*S, lddo]  dO                                           */
+  const float* lse;  /* f32 [B, heads, S] from dod_fmha_fwd                            */
+  float* dsum;       /* f32 [B, heads, S] workspace: rowsum(dO o O)                    */
+  float* dq_acc;     /* f32 [B*S, ld_dq]  zero-initialised; head h at columns h*64      */
+  void* dqkv;        /* bf16 [B*S, ld_dqkv]; dK at k_off + h*64, dV at v_off + h*64     */
+  int64_t batch, seq, heads, ld, ldo, lddo, ld_dq, ld_dqkv;
+  int64_t q_off, k_off, v_off;
+  float scale;
+} dod_fmha_bwd_args;
+DOD_API int32_t dod_fmha_bwd(const dod_fmha_bwd_args* a, dod_stream_t stream);
 
 /* ---- decoder attention with few queries (generic head dim) ---------------
  * nn.MultiheadAttention core (torch) used at deformable_attention.py:232-233

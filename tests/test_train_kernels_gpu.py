@@ -116,6 +116,33 @@ def test_gemm_batched_transposed_views(ops):
     assert _rel(heads(dq3, lq), ds.float() @ k4.float()) < 1e-2
 
 
+@pytest.mark.parametrize("b,s,h", [(2, 257, 3), (1, 1370, 2), (3, 128, 1), (2, 100, 2)])
+def test_fmha_bwd_matches_autograd(ops, b, s, h):
+    """Fused attention backward (recomputed probabilities, TMEM-resident dK/dV, TMA reduce-add dQ)
+    against torch autograd of softmax(QK^T/8)V on the same bf16 inputs."""
+    g = _g(b * 1000 + s)
+    d = h * 64
+    ld = 3 * d + 8                                     # padded row: strides are not the tight ones
+    qkv = torch.zeros((b * s, ld), dtype=torch.bfloat16, device="cuda")
+    qkv[:, :3 * d] = _randn((b * s, 3 * d), g, 0.8).bfloat16()
+    dctx = _randn((b * s, d), g).bfloat16()
+    lse = torch.empty((b, h, s), dtype=torch.float32, device="cuda")
+    ctx = ops.fmha(qkv, b, s, h, q_off=0, k_off=d, v_off=2 * d, scale=0.125, lse=lse)
+    x = qkv[:, :3 * d].float().view(b, s, 3, h, 64).permute(2, 0, 3, 1, 4).detach().requires_grad_(True)
+    sc = (x[0] @ x[1].transpose(-1, -2)) * 0.125
+    ref = torch.softmax(sc, -1) @ x[2]                 # [b, h, s, 64]
+    want_lse = torch.logsumexp(sc, -1) * 1.4426950408889634
+    assert (lse - want_lse).abs().max().item() < 2e-3
+    ref.backward(dctx.float().view(b, s, h, 64).permute(0, 2, 1, 3))
+    dqkv = torch.full((b * s, ld), 7.0, dtype=torch.bfloat16, device="cuda")
+    ops.fmha_bwd(qkv, ctx, dctx, lse, dqkv, b, s, h, q_off=0, k_off=d, v_off=2 * d, scale=0.125)
+    got = dqkv[:, :3 * d].float().view(b, s, 3, h, 64).permute(2, 0, 3, 1, 4)
+    for i, name in enumerate(("dq", "dk", "dv")):
+        err = _rel(got[i], x.grad[i])
+        assert err < 2e-2, (name, err)
+    assert (dqkv[:, 3 * d:] == 7.0).all()              # padding columns untouched
+
+
 def test_transpose(ops):
     g = _g(1)
     x = _randn((3, 257, 100), g).bfloat16()
