@@ -196,61 +196,137 @@ __device__ __forceinline__ uint32_t hash32(uint64_t v) {  // splitmix-style coun
   return uint32_t((v ^ (v >> 31)) >> 32);
 }
 
+// 8 consecutive elements of a row per thread: 16-byte (bf16) / 2 x 16-byte (f32) accesses when the
+// caller's pointers and leading dimensions allow it (VEC), scalar accesses otherwise.
+template <bool VEC>
+__device__ __forceinline__ void ld8(const void* p, int64_t off, int dt, int n, float (&v)[8]) {
+  if (VEC) {
+    if (dt == DOD_BF16) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p) + off);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+      }
+    } else {
+      const float4 lo = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + off);
+      const float4 hi = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + off + 4);
+      v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+      v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = i < n ? ldv(p, off + i, dt) : 0.f;
+  }
+}
+template <bool VEC>
+__device__ __forceinline__ void st8(void* p, int64_t off, int dt, int n, const float (&v)[8]) {
+  if (VEC) {
+    if (dt == DOD_BF16) {
+      uint4 raw;
+      raw.x = pack_bf16x2(v[0], v[1]);
+      raw.y = pack_bf16x2(v[2], v[3]);
+      raw.z = pack_bf16x2(v[4], v[5]);
+      raw.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p) + off) = raw;
+    } else {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + off) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p) + off + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < n) stv(p, off + i, dt, v[i]);
+  }
+}
+
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 eltwise_kernel(int mode, const void* __restrict__ a, int a_dt, const void* __restrict__ b, int b_dt,
                const float* __restrict__ vec, void* __restrict__ out, int out_dt, void* __restrict__ out2,
                int out2_dt, int64_t rows, int cols, int64_t ld_a, int64_t ld_b, int64_t ld_out,
                float p0, uint64_t seed) {
-  const int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x;
-  if (i >= rows * cols) return;
-  const int64_t r = i / cols;
-  const int c = int(i - r * cols);
+  const int gpr = (cols + 7) >> 3;  // 8-element groups per row
+  const int64_t g = int64_t(blockIdx.x) * 256 + threadIdx.x;
+  if (g >= rows * gpr) return;
+  const int64_t r = g / gpr;
+  const int c = int(g - r * gpr) << 3;
+  const int n = min(8, cols - c);
+  float x[8], y[8], o[8];
+  ld8<VEC>(a, r * ld_a + c, a_dt, n, x);
   switch (mode) {
-    case DOD_ELT_CAST: stv(out, r * ld_out + c, out_dt, ldv(a, r * ld_a + c, a_dt)); break;
-    case DOD_ELT_SCALE_COLS:  // out = a * vec[c]
-      stv(out, r * ld_out + c, out_dt, ldv(a, r * ld_a + c, a_dt) * vec[c]);
+    case DOD_ELT_CAST:
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = x[i];
       break;
-    case DOD_ELT_ADD: stv(out, r * ld_out + c, out_dt, ldv(a, r * ld_a + c, a_dt) + ldv(b, r * ld_b + c, b_dt)); break;
-    case DOD_ELT_GELU_FWD: stv(out, r * ld_out + c, out_dt, gelu_f(ldv(a, r * ld_a + c, a_dt))); break;
+    case DOD_ELT_SCALE_COLS:  // out = a * vec[c]
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = i < n ? x[i] * vec[c + i] : 0.f;
+      break;
+    case DOD_ELT_ADD:
+      ld8<VEC>(b, r * ld_b + c, b_dt, n, y);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = x[i] + y[i];
+      break;
+    case DOD_ELT_GELU_FWD:
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = gelu_f(x[i]);
+      break;
     case DOD_ELT_GELU_BWD:  // a = upstream grad, b = pre-activation
-      stv(out, r * ld_out + c, out_dt, ldv(a, r * ld_a + c, a_dt) * gelu_grad(ldv(b, r * ld_b + c, b_dt)));
+      ld8<VEC>(b, r * ld_b + c, b_dt, n, y);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = x[i] * gelu_grad(y[i]);
       break;
     case DOD_ELT_RELU_BWD:  // a = upstream grad, b = activation output
-      stv(out, r * ld_out + c, out_dt, ldv(b, r * ld_b + c, b_dt) > 0.f ? ldv(a, r * ld_a + c, a_dt) : 0.f);
+      ld8<VEC>(b, r * ld_b + c, b_dt, n, y);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = y[i] > 0.f ? x[i] : 0.f;
       break;
-    case DOD_ELT_SIGMOID_BWD: {  // a = upstream grad, b = sigmoid output
-      const float y = ldv(b, r * ld_b + c, b_dt);
-      stv(out, r * ld_out + c, out_dt, ldv(a, r * ld_a + c, a_dt) * y * (1.0f - y));
+    case DOD_ELT_SIGMOID_BWD:  // a = upstream grad, b = sigmoid output
+      ld8<VEC>(b, r * ld_b + c, b_dt, n, y);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = x[i] * y[i] * (1.0f - y[i]);
       break;
-    }
-    case DOD_ELT_SWIGLU_FWD: {  // a = [rows, 2*cols] (gate | linear), out = silu(gate) * linear
-      const float g = ldv(a, r * ld_a + c, a_dt), u = ldv(a, r * ld_a + cols + c, a_dt);
-      stv(out, r * ld_out + c, out_dt, g / (1.0f + expf(-g)) * u);
+    case DOD_ELT_SWIGLU_FWD:  // a = [rows, 2*cols] (gate | linear), out = silu(gate) * linear
+      ld8<VEC>(a, r * ld_a + cols + c, a_dt, n, y);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = x[i] / (1.0f + expf(-x[i])) * y[i];
       break;
-    }
     case DOD_ELT_SWIGLU_BWD: {  // a = upstream [rows, cols], b = pre-activation [rows, 2*cols]; out [rows, 2*cols]
-      const float g = ldv(b, r * ld_b + c, b_dt), u = ldv(b, r * ld_b + cols + c, b_dt);
-      const float dy = ldv(a, r * ld_a + c, a_dt);
-      const float sg = 1.0f / (1.0f + expf(-g));
-      stv(out, r * ld_out + c, out_dt, dy * u * (sg * (1.0f + g * (1.0f - sg))));
-      stv(out, r * ld_out + cols + c, out_dt, dy * g * sg);
+      float gt[8], o2[8];
+      ld8<VEC>(b, r * ld_b + c, b_dt, n, gt);
+      ld8<VEC>(b, r * ld_b + cols + c, b_dt, n, y);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float sg = 1.0f / (1.0f + expf(-gt[i]));
+        o[i] = x[i] * y[i] * (sg * (1.0f + gt[i] * (1.0f - sg)));
+        o2[i] = x[i] * gt[i] * sg;
+      }
+      st8<VEC>(out, r * ld_out + cols + c, out_dt, n, o2);
       break;
     }
-    case DOD_ELT_DROPOUT: {  // out = a * keep / (1 - p); the mask is a pure function of (seed, i)
-      const float keep = (hash32(seed + uint64_t(i)) >> 8) * (1.0f / 16777216.0f) >= p0 ? 1.0f / (1.0f - p0) : 0.f;
-      const float v = ldv(a, r * ld_a + c, a_dt) * keep;
-      stv(out, r * ld_out + c, out_dt, v);
-      if (out2) stv(out2, r * ld_out + c, out2_dt, v);
+    case DOD_ELT_DROPOUT: {  // out = a * keep / (1 - p); the mask is a pure function of (seed, element index)
+      const uint64_t i0 = uint64_t(r) * uint64_t(cols) + uint64_t(c);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        o[i] = (hash32(seed + i0 + i) >> 8) * (1.0f / 16777216.0f) >= p0 ? x[i] * (1.0f / (1.0f - p0)) : 0.f;
+      if (out2) st8<VEC>(out2, r * ld_out + c, out2_dt, n, o);
       break;
     }
-    case DOD_ELT_AXPBY: {
-      float v = vec[0] * ldv(a, r * ld_a + c, a_dt);
-      if (b) v += vec[1] * ldv(b, r * ld_b + c, b_dt);
-      stv(out, r * ld_out + c, out_dt, v);
+    case DOD_ELT_AXPBY:
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = vec[0] * x[i];
+      if (b) {
+        ld8<VEC>(b, r * ld_b + c, b_dt, n, y);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += vec[1] * y[i];
+      }
       break;
-    }
-    default: break;
+    default: return;
   }
+  st8<VEC>(out, r * ld_out + c, out_dt, n, o);
 }
 
 // ------------------------------------------------------------------ softmax rows
@@ -481,8 +557,16 @@ extern "C" int32_t dod_eltwise(const dod_eltwise_args* a, dod_stream_t stream_) 
   DOD_REQUIRE(a->mode >= DOD_ELT_CAST && a->mode <= DOD_ELT_AXPBY, "dod_eltwise: bad mode");
   DOD_REQUIRE(a->rows >= 0 && a->cols > 0, "dod_eltwise: bad shape");
   if (a->rows == 0) return DOD_OK;
-  const int64_t total = a->rows * a->cols;
-  eltwise_kernel<<<unsigned((total + 255) / 256), 256, 0, stream>>>(
+  const int64_t total = a->rows * ((a->cols + 7) / 8);
+  DOD_REQUIRE((total + 255) / 256 < (int64_t(1) << 31), "dod_eltwise: too many elements");
+  // 16-byte accesses need every operand row to start 16-byte aligned and whole 8-element groups
+  auto vec_ok = [](const void* p, int64_t ld, int dt) {
+    return p == nullptr || ((uintptr_t(p) & 15) == 0 && ld % (dt == DOD_BF16 ? 8 : 4) == 0);
+  };
+  const bool vec = a->cols % 8 == 0 && vec_ok(a->a, a->ld_a, a->a_dtype) && vec_ok(a->b, a->ld_b, a->b_dtype) &&
+                   vec_ok(a->out, a->ld_out, a->out_dtype) && vec_ok(a->out2, a->ld_out, a->out2_dtype);
+  auto kern = vec ? eltwise_kernel<true> : eltwise_kernel<false>;
+  kern<<<unsigned((total + 255) / 256), 256, 0, stream>>>(
       a->mode, a->a, a->a_dtype, a->b, a->b_dtype, a->vec, a->out, a->out_dtype, a->out2, a->out2_dtype,
       a->rows, int(a->cols), a->ld_a, a->ld_b, a->ld_out, a->p0, uint64_t(a->seed));
   int rc = check_cuda(cudaGetLastError(), "eltwise_kernel launch");

@@ -121,22 +121,32 @@ def _ptr(x):
     return x.data_ptr()  # torch.Tensor
 
 
+_OP_CACHE = {}   # fn -> (struct type, {field: is_pointer}, bound C function)
+
+
 def call(fn: str, stream: int, **fields):
-    """Fill dod_<op>_args from keyword arguments and launch on `stream`."""
-    l = lib()
-    st = _OP_STRUCT[fn]()
-    for name, ctype in st._fields_:
-        if name not in fields:
-            continue
-        v = fields.pop(name)
-        if ctype is ctypes.c_void_p:
-            v = _ptr(v)
-        setattr(st, name, v)
-    if fields:
-        raise TypeError(f"{fn}: unknown fields {sorted(fields)}")
-    rc = getattr(l, fn)(ctypes.byref(st), ctypes.c_void_p(stream))
+    """Fill dod_<op>_args from keyword arguments and launch on `stream`.  Only the fields given are
+    touched (ctypes zero-initialises the rest): this runs once per kernel launch, so it is kept short."""
+    ent = _OP_CACHE.get(fn)
+    if ent is None:
+        l = lib()
+        stype = _OP_STRUCT[fn]
+        ent = _OP_CACHE[fn] = (stype, {n: t is ctypes.c_void_p for n, t in stype._fields_}, getattr(l, fn))
+    stype, is_ptr, cfn = ent
+    st = stype()
+    try:
+        for name, v in fields.items():
+            if is_ptr[name]:
+                if v is None:
+                    continue
+                if not isinstance(v, int):
+                    v = v.data_ptr()  # torch.Tensor
+            setattr(st, name, v)
+    except KeyError:
+        raise TypeError(f"{fn}: unknown fields {sorted(set(fields) - set(is_ptr))}") from None
+    rc = cfn(ctypes.byref(st), stream)
     if rc != 0:
-        raise DodError(f"{fn} failed ({rc}): {l.dod_last_error().decode()}")
+        raise DodError(f"{fn} failed ({rc}): {lib().dod_last_error().decode()}")
 
 
 def launch_count() -> int:

@@ -206,6 +206,14 @@ def test_eltwise_modes(ops):
     assert torch.equal(ops.eltwise(ops.ELT_RELU_BWD, b, relu, out_dtype=torch.float32), b * (relu > 0))
     sg = torch.sigmoid(a)
     assert torch.allclose(ops.eltwise(ops.ELT_SIGMOID_BWD, b, sg, out_dtype=torch.float32), b * sg * (1 - sg), atol=1e-6)
+    # ragged width (scalar path: 91 columns, rows not 16-byte aligned) and strided views (vector path)
+    odd = _randn((33, 91), g)
+    assert torch.equal(ops.eltwise(ops.ELT_CAST, odd, out_dtype=torch.bfloat16), odd.bfloat16())
+    assert torch.allclose(ops.eltwise(ops.ELT_ADD, odd, odd, out_dtype=torch.float32), 2 * odd)
+    wide = _randn((rows, 3 * cols), g)
+    dst = torch.zeros((rows, 2 * cols), dtype=torch.bfloat16, device="cuda")
+    ops.eltwise(ops.ELT_CAST, wide[:, cols:2 * cols], out=dst[:, cols:])
+    assert torch.equal(dst[:, cols:], wide[:, cols:2 * cols].bfloat16()) and (dst[:, :cols] == 0).all()
     # SwiGLU
     zz = _randn((rows, 2 * cols), g).requires_grad_(True)
     x1, x2 = zz.chunk(2, dim=-1)

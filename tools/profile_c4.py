@@ -45,3 +45,26 @@ print(json.dumps({"batch": batch, "wall_ms_per_step": wall, "gpu_kernel_ms_per_s
 for e in sorted(ev, key=lambda e: -e.device_time_total)[:25]:
     print(f"{e.device_time_total / 3 / 1e3:8.3f} ms  x{e.count // 3:4d}  {e.key[:110]}")
 print("kernel launches per step:", sum(e.count for e in ev) // 3)
+
+# ---- per-mode breakdown of the elementwise launches (CUDA events around each call) ----
+from dino_detector import ops as _ops
+_rec = []
+_orig = _ops.eltwise
+def _wrapped(mode, a, *args, **kw):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = _orig(mode, a, *args, **kw)
+    e1.record()
+    _rec.append((mode, tuple(a.shape), str(a.dtype), e0, e1))
+    return r
+_ops.eltwise = _wrapped
+step()
+torch.cuda.synchronize()
+agg = {}
+for mode, shape, dt, e0, e1 in _rec:
+    k = (mode, shape, dt)
+    n, t = agg.get(k, (0, 0.0))
+    agg[k] = (n + 1, t + e0.elapsed_time(e1))
+names = {getattr(_ops, n): n for n in dir(_ops) if n.startswith("ELT_")}
+for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]:
+    print(f"{t:7.3f} ms x{n:3d} {names.get(k[0], k[0])} {k[1]} {k[2]}")
