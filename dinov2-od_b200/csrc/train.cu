@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(256)
 eltwise_kernel(int mode, const void* __restrict__ a, int a_dt, const void* __restrict__ b, int b_dt,
                const float* __restrict__ vec, void* __restrict__ out, int out_dt, void* __restrict__ out2,
                int out2_dt, int64_t rows, int cols, int64_t ld_a, int64_t ld_b, int64_t ld_out,
-               float p0, uint64_t seed) {
+               float p0, uint64_t seed, const int64_t* __restrict__ seed_ptr) {
   const int gpr = (cols + 7) >> 3;  // 8-element groups per row
   const int64_t g = int64_t(blockIdx.x) * 256 + threadIdx.x;
   if (g >= rows * gpr) return;
@@ -308,6 +308,7 @@ eltwise_kernel(int mode, const void* __restrict__ a, int a_dt, const void* __res
       break;
     }
     case DOD_ELT_DROPOUT: {  // out = a * keep / (1 - p); the mask is a pure function of (seed, element index)
+      if (seed_ptr != nullptr) seed += uint64_t(*seed_ptr) << 44;
       const uint64_t i0 = uint64_t(r) * uint64_t(cols) + uint64_t(c);
 #pragma unroll
       for (int i = 0; i < 8; ++i)
@@ -333,7 +334,9 @@ eltwise_kernel(int mode, const void* __restrict__ a, int a_dt, const void* __res
 // P[row, :n] = softmax(scale * S[row, :n]) (bf16, zero padded to ldp); optional prob dropout.
 __global__ void __launch_bounds__(256)
 softmax_rows_kernel(const void* __restrict__ s, int s_dt, __nv_bfloat16* __restrict__ p, int64_t rows,
-                    int n, int64_t lds, int64_t ldp, float scale, float drop_p, uint64_t seed) {
+                    int n, int64_t lds, int64_t ldp, float scale, float drop_p, uint64_t seed,
+                    const int64_t* __restrict__ seed_ptr) {
+  if (seed_ptr != nullptr) seed += uint64_t(*seed_ptr) << 44;
   const int lane = threadIdx.x & 31;
   const int64_t row = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -360,7 +363,9 @@ softmax_rows_kernel(const void* __restrict__ s, int s_dt, __nv_bfloat16* __restr
 __global__ void __launch_bounds__(256)
 softmax_bwd_rows_kernel(const __nv_bfloat16* __restrict__ p, const void* __restrict__ dp, int dp_dt,
                         __nv_bfloat16* __restrict__ ds, int64_t rows, int n, int64_t ldp, int64_t lddp,
-                        int64_t ldds, float scale, float drop_p, uint64_t seed) {
+                        int64_t ldds, float scale, float drop_p, uint64_t seed,
+                        const int64_t* __restrict__ seed_ptr) {
+  if (seed_ptr != nullptr) seed += uint64_t(*seed_ptr) << 44;
   const int lane = threadIdx.x & 31;
   const int64_t row = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -568,7 +573,7 @@ extern "C" int32_t dod_eltwise(const dod_eltwise_args* a, dod_stream_t stream_) 
   auto kern = vec ? eltwise_kernel<true> : eltwise_kernel<false>;
   kern<<<unsigned((total + 255) / 256), 256, 0, stream>>>(
       a->mode, a->a, a->a_dtype, a->b, a->b_dtype, a->vec, a->out, a->out_dtype, a->out2, a->out2_dtype,
-      a->rows, int(a->cols), a->ld_a, a->ld_b, a->ld_out, a->p0, uint64_t(a->seed));
+      a->rows, int(a->cols), a->ld_a, a->ld_b, a->ld_out, a->p0, uint64_t(a->seed), a->seed_ptr);
   int rc = check_cuda(cudaGetLastError(), "eltwise_kernel launch");
   if (rc == 0) count_launch();
   return rc;
@@ -580,7 +585,7 @@ extern "C" int32_t dod_softmax_rows(const dod_softmax_rows_args* a, dod_stream_t
   DOD_REQUIRE(a->rows > 0 && a->n > 0 && a->lds >= a->n && a->ldp >= a->n, "dod_softmax_rows: bad shape");
   softmax_rows_kernel<<<unsigned((a->rows + 7) / 8), 256, 0, stream>>>(
       a->s, a->s_dtype, (__nv_bfloat16*)a->p, a->rows, int(a->n), a->lds, a->ldp, a->scale, a->drop_p,
-      uint64_t(a->seed));
+      uint64_t(a->seed), a->seed_ptr);
   int rc = check_cuda(cudaGetLastError(), "softmax_rows_kernel launch");
   if (rc == 0) count_launch();
   return rc;
@@ -593,7 +598,7 @@ extern "C" int32_t dod_softmax_bwd_rows(const dod_softmax_bwd_rows_args* a, dod_
               "dod_softmax_bwd_rows: bad shape");
   softmax_bwd_rows_kernel<<<unsigned((a->rows + 7) / 8), 256, 0, stream>>>(
       (const __nv_bfloat16*)a->p, a->dp, a->dp_dtype, (__nv_bfloat16*)a->ds, a->rows, int(a->n), a->ldp,
-      a->lddp, a->ldds, a->scale, a->drop_p, uint64_t(a->seed));
+      a->lddp, a->ldds, a->scale, a->drop_p, uint64_t(a->seed), a->seed_ptr);
   int rc = check_cuda(cudaGetLastError(), "softmax_bwd_rows_kernel launch");
   if (rc == 0) count_launch();
   return rc;

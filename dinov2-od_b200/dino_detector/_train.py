@@ -417,7 +417,8 @@ def train_forward(model, pixel_values):
     dh = hd // nh
     scale = 1.0 / math.sqrt(dh)
     p_drop = float(dec.dropout_p) if dec.training else 0.0
-    st.p_drop, st.seed = p_drop, next(_seed_counter) << 44
+    # with a device seed counter (graph replay) the per-step part of the seed lives on the device
+    st.p_drop, st.seed = p_drop, (0 if ops.device_seed() is not None else next(_seed_counter) << 44)
     st.q, st.hd, st.nh, st.dh, st.scale = q, hd, nh, dh, scale
     st.deformable = dec.use_deformable
     layers = list(dec.decoder.layers)

@@ -57,17 +57,25 @@ class SetCriterion(nn.Module):
         self.strict = True
 
     def forward(self, outputs, targets):
-        logits, boxes = outputs["pred_logits"], outputs["pred_boxes"]
-        dev = logits.device
+        dev = outputs["pred_logits"].device
         if not isinstance(self.matcher, HungarianMatcher):
             raise TypeError("SetCriterion needs the libdod HungarianMatcher (device-resident assignment)")
         packed = self.matcher.pack_targets(targets, dev)
-        out_q, out_t, status, counts, _ = self.matcher.match_device(outputs, targets, packed=packed)
+        # losses.py:225-230: num_boxes = sum of GT counts
+        num_boxes = torch.tensor([float(sum(packed[3]))], dtype=torch.float32).to(dev, non_blocking=True)
+        return self.forward_packed(outputs, packed, num_boxes)
+
+    def forward_packed(self, outputs, packed, num_boxes):
+        """Device-only form (no host reads; capturable in a CUDA graph when strict is False):
+        packed = (labels i64 [T], boxes f32 [T, 4], offsets i32 [B + 1], per-image counts or None,
+        max targets per image); num_boxes = f32 [1] device tensor with this rank's GT count."""
+        logits, boxes = outputs["pred_logits"], outputs["pred_boxes"]
+        out_q, out_t, status, _, _ = self.matcher.match_device(outputs, None, packed=packed)
         if self.strict and bool((status != 0).any()):
             raise ValueError("matrix contains invalid numeric entries")
-        # losses.py:225-230: num_boxes = sum of GT counts, all-reduced with SUM (no / world), clamp(min=1)
-        num_boxes = torch.tensor([float(sum(packed[3]))], dtype=torch.float32).to(dev, non_blocking=True)
+        # losses.py:228-230: all-reduced with SUM (no / world), clamp(min=1)
         if dist.is_available() and dist.is_initialized():
+            num_boxes = num_boxes.clone()
             dist.all_reduce(num_boxes)
         num_boxes = torch.clamp(num_boxes, min=1)
         l_ce, l_bbox, l_giou = _CriterionFn.apply(logits, boxes, self, packed, out_q, out_t, num_boxes)

@@ -55,13 +55,13 @@ class HungarianMatcher(nn.Module):
         logits = logits.float().contiguous()
         boxes = boxes.float().contiguous()
         labels, tboxes, offsets, ns, max_t = packed if packed is not None else self.pack_targets(targets, dev)
-        assert len(ns) == bs, "one target dict per image"
+        assert offsets.numel() == bs + 1, "one target dict per image"
         cost = ops.match_cost(logits, boxes, labels, tboxes, offsets, max_t,
                               w_class=float(self.cost_class), w_bbox=float(self.cost_bbox),
                               w_giou=float(self.cost_giou), alpha=float(self.focal_alpha),
                               gamma=float(self.focal_gamma), use_image0_rows=self.reference_compat)
         out_q, out_t, status = ops.lsap(cost, offsets, max_t)
-        counts = [min(nq, n) for n in ns]
+        counts = [min(nq, n) for n in ns] if ns is not None else None
         return out_q, out_t, status, counts, cost
 
     @torch.no_grad()

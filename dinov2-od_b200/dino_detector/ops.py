@@ -289,6 +289,30 @@ ELT_CAST, ELT_SCALE_COLS, ELT_ADD, ELT_GELU_FWD, ELT_GELU_BWD, ELT_RELU_BWD, ELT
     ELT_SWIGLU_FWD, ELT_SWIGLU_BWD, ELT_DROPOUT, ELT_AXPBY = range(11)
 
 
+# Device-resident dropout seed counter (runtime.GraphedTrainStep): when set, the dropout / attention
+# dropout kernels add (*counter << 44) to their launch-time seed, so a replayed CUDA graph draws a new
+# mask every step although its launch arguments are frozen.
+_seed_ptr = None
+
+
+def set_device_seed(counter):
+    """counter: int64 CUDA tensor [>= 1] (element 0 is used) or None to return to host-side seeds."""
+    global _seed_ptr
+    if counter is not None:
+        assert counter.dtype == torch.int64 and counter.is_cuda
+    _seed_ptr = counter
+
+
+def device_seed():
+    return _seed_ptr
+
+
+def counter_add(counters, delta=1):
+    """counters[:] += delta on the device (int64, <= 32 elements)."""
+    assert counters.dtype == torch.int64 and counters.is_contiguous()
+    _dod.call("dod_counter_add", _stream(counters), counters=counters, n=counters.numel(), delta=delta)
+
+
 def gemm_batched(a, w, out, *, bias=None, act=ACT_NONE, a_trans=False, w_trans=False):
     """out[..] = act(a[..] @ w[..].T + bias) over one or two leading batch dims:
     a [B, M, K] / [B, H, M, K], w [B, N, K] / [B, H, N, K], out [B, M, N] / [B, H, M, N]; strided views
@@ -386,7 +410,8 @@ def eltwise(mode, a, b=None, *, vec=None, out_dtype=None, out=None, cols=None, p
               b_dtype=_DT[b.dtype] if b is not None else 0, vec=vec, out=out, out_dtype=_DT[out.dtype],
               out2=out2, out2_dtype=_DT[out2.dtype] if out2 is not None else 0, rows=rows, cols=cols,
               ld_a=_rowmajor(a, "a"), ld_b=_rowmajor(b, "b") if b is not None else 0,
-              ld_out=_rowmajor(out, "out"), p0=p0, seed=seed)
+              ld_out=_rowmajor(out, "out"), p0=p0, seed=seed,
+              seed_ptr=_seed_ptr if mode == ELT_DROPOUT else None)
     return (out, out2) if out2 is not None else out
 
 
@@ -396,7 +421,8 @@ def softmax_rows(s, n, scale, *, ldp=None, drop_p=0.0, seed=0):
     ldp = ldp or (n + 7) // 8 * 8
     p = torch.empty((rows, ldp), dtype=torch.bfloat16, device=s.device)
     _dod.call("dod_softmax_rows", _stream(s), s=s, s_dtype=_DT[s.dtype], p=p, rows=rows, n=n,
-              lds=_rowmajor(s, "s"), ldp=ldp, scale=scale, drop_p=drop_p, seed=seed)
+              lds=_rowmajor(s, "s"), ldp=ldp, scale=scale, drop_p=drop_p, seed=seed,
+              seed_ptr=_seed_ptr if drop_p > 0 else None)
     return p
 
 
@@ -405,7 +431,7 @@ def softmax_bwd_rows(p, dp, n, scale, *, drop_p=0.0, seed=0):
     ds = torch.empty_like(p)
     _dod.call("dod_softmax_bwd_rows", _stream(p), p=p, dp=dp, dp_dtype=_DT[dp.dtype], ds=ds, rows=rows, n=n,
               ldp=_rowmajor(p, "p"), lddp=_rowmajor(dp, "dp"), ldds=_rowmajor(ds, "ds"), scale=scale,
-              drop_p=drop_p, seed=seed)
+              drop_p=drop_p, seed=seed, seed_ptr=_seed_ptr if drop_p > 0 else None)
     return ds
 
 
@@ -448,12 +474,13 @@ def sumsq(x, out):
 
 
 def adam_step(param, grad, exp_avg, exp_avg_sq, step, *, lr, beta1, beta2, eps, weight_decay,
-              grad_sumsq=None, max_grad_norm=0.0):
+              grad_sumsq=None, max_grad_norm=0.0, step_ptr=None):
+    """step_ptr: optional int64 device counter used instead of `step` (graph replay)."""
     for t in (param, grad, exp_avg, exp_avg_sq):
         assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == param.numel()
     _dod.call("dod_adam_step", _stream(param), param=param, grad=grad, exp_avg=exp_avg, exp_avg_sq=exp_avg_sq,
               n=param.numel(), step=step, grad_sumsq=grad_sumsq, max_grad_norm=max_grad_norm, lr=lr,
-              beta1=beta1, beta2=beta2, eps=eps, weight_decay=weight_decay)
+              beta1=beta1, beta2=beta2, eps=eps, weight_decay=weight_decay, step_ptr=step_ptr)
 
 
 def postprocess(logits, boxes, threshold=0.05):

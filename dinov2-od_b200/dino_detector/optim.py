@@ -36,6 +36,9 @@ class FusedAdam:
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.max_grad_norm = max_grad_norm
         self.step_count = 0
+        # optional int64 device tensor holding the step number (runtime.GraphedTrainStep advances it
+        # inside the captured graph); None = the host-side step_count is passed by value
+        self.device_step = None
 
     def zero_grad(self):
         self.sync.zero()
@@ -51,7 +54,7 @@ class FusedAdam:
         ops.adam_step(self.flat_param, self.sync.flat, self.exp_avg, self.exp_avg_sq, self.step_count,
                       lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
                       weight_decay=self.weight_decay, grad_sumsq=self.norm_sq,
-                      max_grad_norm=float(self.max_grad_norm or 0.0))
+                      max_grad_norm=float(self.max_grad_norm or 0.0), step_ptr=self.device_step)
         # the update went through the flat buffer, not torch's per-tensor version counters
         _engine.bump_weight_epoch()
 

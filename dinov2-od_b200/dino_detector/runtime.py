@@ -1,4 +1,4 @@
-"""CUDA-graph replay of the inference forward for launch-bound (small batch) serving.
+"""CUDA-graph replay of the inference forward and of the whole training step (launch-bound small batches).
 
 The detector forward is ~200 kernel launches; at batch 2 / 224x224 (BASELINE config 1) the GPU work is
 well under the host time needed to issue them.  `GraphedDetector` captures one forward for a fixed
@@ -43,3 +43,121 @@ class GraphedDetector:
         self.static_in.copy_(pixel_values, non_blocking=True)
         self.graph.replay()
         return self.static_out
+
+
+class GraphedTrainStep:
+    """One whole training step -- forward, GPU matcher, fused criterion, hand-written backward, flat
+    gradient all-reduce, global-norm clip + Adam -- captured into ONE CUDA graph and replayed.
+
+    A train step is ~1300 kernel launches issued from Python; below ~16 images per GPU the host cannot
+    issue them as fast as the GPU retires them (profiles/r01_summary.md: L/14, batch 8: 20 ms of kernels in
+    a 31 ms step).  Everything on the step is device-resident already (the assignment never visits the
+    host), so the step replays from a graph once three things live on the device instead of in launch
+    arguments: the dropout seed and the Adam step number (int64 counters advanced inside the graph) and
+    the targets (CSR buffers of fixed capacity that `__call__` refills before each replay).
+
+        step = GraphedTrainStep(model, criterion, FusedAdam(model.parameters(), ...), images, max_targets=100)
+        losses = step(images, targets)     # dict of device scalars (weighted, like SetCriterion.forward)
+
+    Shapes are fixed at capture (batch, H, W, max_targets per image).  The solver status is not checked
+    on the host (criterion.strict is ignored): NaN / infeasible cost matrices leave those images unmatched.
+    Under torch.distributed the NCCL all-reduces (num_boxes, flat gradient) are part of the graph.
+    """
+
+    def __init__(self, model, criterion, optimizer, example_images, max_targets=100, warmup=3):
+        from . import ops
+        from .optim import FusedAdam
+        if not isinstance(optimizer, FusedAdam):
+            raise TypeError("GraphedTrainStep needs optim.FusedAdam (flat device-resident state)")
+        self.model, self.criterion, self.opt = model, criterion, optimizer
+        dev = example_images.device
+        b = example_images.shape[0]
+        self.batch, self.max_t = b, int(max_targets)
+        self.images = example_images.detach().clone().contiguous()
+        cap = b * self.max_t
+        self.labels = torch.zeros(cap, dtype=torch.int64, device=dev)
+        self.boxes = torch.full((cap, 4), 0.5, dtype=torch.float32, device=dev)
+        self.offsets = torch.zeros(b + 1, dtype=torch.int32, device=dev)
+        self.num_boxes = torch.zeros(1, dtype=torch.float32, device=dev)
+        # pinned staging for the per-step target upload (one async copy per buffer)
+        self._h_labels = torch.zeros(cap, dtype=torch.int64).pin_memory()
+        self._h_boxes = torch.zeros((cap, 4), dtype=torch.float32).pin_memory()
+        self._h_offsets = torch.zeros(b + 1, dtype=torch.int32).pin_memory()
+        self._h_num = torch.zeros(1, dtype=torch.float32).pin_memory()
+        # [0] dropout seed epoch, [1] Adam step number; continue from the optimizer's host count
+        self.counters = torch.tensor([1, optimizer.step_count], dtype=torch.int64, device=dev)
+        self._ops = ops
+        self.losses = None
+        self.graph = None
+        self._capture(warmup)
+
+    def _step_body(self):
+        ops = self._ops
+        ops.counter_add(self.counters, 1)
+        self.opt.zero_grad()
+        out = self.model(self.images)
+        packed = (self.labels, self.boxes, self.offsets, None, self.max_t)
+        losses = self.criterion.forward_packed(out, packed, self.num_boxes)
+        total = losses["loss_ce"] + losses["loss_bbox"] + losses["loss_giou"]
+        total.backward()
+        self.opt.step()
+        return {k: v.detach() for k, v in losses.items()}
+
+    def _capture(self, warmup):
+        ops = self._ops
+        dev = self.images.device
+        strict, self.criterion.strict = self.criterion.strict, False
+        ops.set_device_seed(self.counters)
+        self.opt.device_step = self.counters[1:2]
+        # the warm-up steps really run (on the example images, no targets): snapshot the optimizer's
+        # flat state and the counters so that capturing does not train the model
+        opt = self.opt
+        snap = [t.clone() for t in (opt.flat_param, opt.exp_avg, opt.exp_avg_sq, self.counters)]
+        try:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(max(1, warmup)):        # kernel attributes, allocator pools, NCCL warm-up
+                    self._step_body()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.losses = self._step_body()
+            for dst, src in zip((opt.flat_param, opt.exp_avg, opt.exp_avg_sq, self.counters), snap):
+                dst.copy_(src)
+        finally:
+            ops.set_device_seed(None)
+            self.opt.device_step = None
+            self.criterion.strict = strict
+        self.opt.step_count = int(self.counters[1].item())
+
+    def load_targets(self, targets):
+        """Refill the static CSR target buffers from a list of target dicts (dataset.py:102-111)."""
+        if len(targets) != self.batch:
+            raise ValueError(f"graph was captured for {self.batch} images, got {len(targets)} target dicts")
+        off = 0
+        self._h_offsets[0] = 0
+        for i, t in enumerate(targets):
+            n = int(t["labels"].shape[0])
+            if n > self.max_t:
+                raise ValueError(f"image {i} has {n} targets, the graph was captured for at most {self.max_t}")
+            if n:
+                self._h_labels[off:off + n].copy_(t["labels"].reshape(-1))
+                self._h_boxes[off:off + n].copy_(t["boxes"].reshape(-1, 4))
+            off += n
+            self._h_offsets[i + 1] = off
+        self._h_num[0] = float(off)
+        self.labels.copy_(self._h_labels, non_blocking=True)
+        self.boxes.copy_(self._h_boxes, non_blocking=True)
+        self.offsets.copy_(self._h_offsets, non_blocking=True)
+        self.num_boxes.copy_(self._h_num, non_blocking=True)
+
+    def __call__(self, images, targets):
+        if tuple(images.shape) != tuple(self.images.shape):
+            raise ValueError(f"graph was captured for images of shape {tuple(self.images.shape)}, got {tuple(images.shape)}")
+        self.images.copy_(images, non_blocking=True)
+        self.load_targets(targets)
+        self.graph.replay()
+        self.opt.step_count += 1
+        return self.losses

@@ -315,6 +315,9 @@ typedef struct {
   void* out2; int32_t out2_dtype;        /* DROPOUT: optional second copy (other dtype)         */
   int64_t rows, cols, ld_a, ld_b, ld_out;
   float p0; int64_t seed;
+  /* optional device counter (CUDA-graph replay: the mask must change between replays although the
+   * launch arguments are frozen): the effective seed is  seed + (*seed_ptr << 44).            */
+  const int64_t* seed_ptr;
 } dod_eltwise_args;
 DOD_API int32_t dod_eltwise(const dod_eltwise_args* a, dod_stream_t stream);
 
@@ -322,6 +325,7 @@ DOD_API int32_t dod_eltwise(const dod_eltwise_args* a, dod_stream_t stream);
 typedef struct {
   const void* s; int32_t s_dtype; void* p;
   int64_t rows, n, lds, ldp; float scale; float drop_p; int64_t seed;
+  const int64_t* seed_ptr;   /* optional device counter, see dod_eltwise_args */
 } dod_softmax_rows_args;
 DOD_API int32_t dod_softmax_rows(const dod_softmax_rows_args* a, dod_stream_t stream);
 /* dS = scale * P * (dP' - rowsum(P * dP')) as bf16 (zero padded to ldds); P is the probability
@@ -330,6 +334,7 @@ DOD_API int32_t dod_softmax_rows(const dod_softmax_rows_args* a, dod_stream_t st
 typedef struct {
   const void* p; const void* dp; int32_t dp_dtype; void* ds;
   int64_t rows, n, ldp, lddp, ldds; float scale; float drop_p; int64_t seed;
+  const int64_t* seed_ptr;   /* optional device counter, see dod_eltwise_args */
 } dod_softmax_bwd_rows_args;
 DOD_API int32_t dod_softmax_bwd_rows(const dod_softmax_bwd_rows_args* a, dod_stream_t stream);
 
@@ -431,8 +436,14 @@ typedef struct {
   const float* grad_sumsq;       /* device float: sum of squared gradients      */
   float max_grad_norm;           /* <= 0: no clipping                           */
   float lr, beta1, beta2, eps, weight_decay;
+  const int64_t* step_ptr;       /* optional device step counter (>= 1) used instead of `step`
+                                    (CUDA-graph replay of the train step)        */
 } dod_adam_args;
 DOD_API int32_t dod_adam_step(const dod_adam_args* a, dod_stream_t stream);
+/* counters[i] += delta for i < n: the device-resident step / seed counters a captured train step
+ * advances once per replay.                                                                    */
+typedef struct { int64_t* counters; int64_t n; int64_t delta; } dod_counter_add_args;
+DOD_API int32_t dod_counter_add(const dod_counter_add_args* a, dod_stream_t stream);
 
 #ifdef __cplusplus
 }

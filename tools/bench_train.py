@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--model", default="facebook/dinov2-large")
     ap.add_argument("--lora-r", type=int, default=8)
+    ap.add_argument("--hw", type=int, default=518, help="image side")
+    ap.add_argument("--graph", action="store_true", help="replay the step from one CUDA graph (runtime.GraphedTrainStep)")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -48,7 +50,7 @@ def main():
     opt = FusedAdam(model.parameters(), lr=1e-4, weight_decay=1e-4, max_grad_norm=1.0)
     sync = opt.sync
     g = torch.Generator().manual_seed(100 + rank)
-    x = torch.rand(a.batch, 3, 518, 518, generator=g).cuda()
+    x = torch.rand(a.batch, 3, a.hw, a.hw, generator=g).cuda()
     targets = [{k: v.cuda() for k, v in t.items()}
                for t in synth.make_targets(a.batch, max_gt=20, seed=3 + rank, min_gt=1)]
 
@@ -58,6 +60,15 @@ def main():
         loss.backward()
         opt.step()
         return loss
+
+    if a.graph:
+        from dino_detector.runtime import GraphedTrainStep
+        graphed = GraphedTrainStep(model, crit, opt, x, max_targets=20)
+        host_targets = [{k: v.cpu() for k, v in t.items()} for t in targets]
+
+        def step():  # noqa: F811  (refills the static image / target buffers, then one graph launch)
+            ld = graphed(x, host_targets)
+            return ld["loss_ce"] + ld["loss_bbox"] + ld["loss_giou"]
 
     for _ in range(a.warmup):
         step()
@@ -75,12 +86,19 @@ def main():
         dist.barrier()
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print(json.dumps({"config": f"c4 {a.model} LoRA r={a.lora_r} + deformable decoder train step, bf16, 518x518",
-                          "n_gpus": world, "batch_per_gpu": a.batch, "ms_per_step": ms.item(),
+        print(json.dumps({"config": f"c4 {a.model} LoRA r={a.lora_r} + deformable decoder train step, bf16, {a.hw}x{a.hw}",
+                          "n_gpus": world, "batch_per_gpu": a.batch, "cuda_graph": bool(a.graph), "ms_per_step": ms.item(),
                           "images_per_s": world * a.batch / (ms.item() * 1e-3), "scaling": "weak",
                           "loss": float(loss), "trainable_params": sync.numel,
                           "grad_allreduce_bytes": sync.numel * 4}))
     if world > 1:
+        if a.graph:
+            # tearing the communicator down while captured graphs still hold NCCL kernels hangs in
+            # destroy_process_group (torch 2.11 / NCCL 2.28): leave together and skip the teardown
+            dist.barrier()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            os._exit(0)
         dist.destroy_process_group()
 
 
