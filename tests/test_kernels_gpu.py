@@ -182,7 +182,7 @@ def test_fmha(ops, b, s, h):
 
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32])
 @pytest.mark.parametrize("b,lq,lk,h,dh", [(2, 50, 50, 8, 96), (3, 100, 257, 4, 64), (1, 25, 1370, 8, 96),
-                                          (2, 17, 33, 4, 192)])
+                                          (2, 17, 33, 4, 192), (1, 100, 100, 8, 96), (2, 128, 128, 4, 64)])
 def test_mha_small(ops, dt, b, lq, lk, h, dh):
     g = _gen(lq + lk)
     d = h * dh
