@@ -241,10 +241,16 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
     float m_used = -INFINITY;  // in log2 units (already scaled)
     float l = 0.0f;            // partial row sum over this thread's columns
 
+    // s_ready / o_ready: the barrier was already seen complete by an early non-blocking test issued
+    // in the middle of the previous / this exp2 phase (the MUFU pipe is the limiter there, the ~100-cycle
+    // barrier instruction hides under it)
+    bool s_ready = false;
     for (int j = 0; j < n_kv; ++j) {
       TRACE(half, j, 0, 0);
-      mbar_wait(s_full, j & 1);
+      if (!s_ready) mbar_wait(s_full, j & 1);
       tc_fence_after();
+      bool o_ready = j == 0;
+      s_ready = false;
       TRACE(half, j, 1, 0);
       const int valid = p.seq - j * kTile - half * 64;  // keys valid in this thread's 64 columns
       // kPolyMask == 0 (default): S is read from TMEM once and held in 64 registers.  The polynomial
@@ -346,12 +352,16 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
           sum2 = __fadd2_rn(sum2, e);
           pk[pi] = pack_bf16x2(e.x, e.y);
         }
+        if (c == 0) {
+          if (j > 0) o_ready = mbar_test_wait(o_full, (j - 1) & 1);
+          if (j + 1 < n_kv) s_ready = mbar_test_wait(s_full, (j + 1) & 1);
+        }
       }
       l = l * alpha + (sum2.x + sum2.y);
       TRACE(half, j, 4, pk[31] ^ pk[15] ^ __float_as_uint(l));
 
       if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1);  // P.V of the previous tile retired
+        if (!o_ready) mbar_wait(o_full, (j - 1) & 1);  // P.V of the previous tile retired
         tc_fence_after();
         TRACE(half, j, 5, 0);
         if (__any_sync(0xffffffffu, bump)) {
@@ -408,6 +418,7 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
     tmem_dealloc<kTmemCols>(tmem);
   }
 }
+
 
 }  // namespace
 }  // namespace dod

@@ -119,6 +119,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking phase test (no hardware sleep): lets a warp look at a barrier early, under work it
+// has to do anyway, and skip the ~100-cycle wait instruction later if the phase already completed.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug traps (launch fails with an error) instead of
 // hanging the GPU.  try_wait sleeps in hardware, so the bound is generous.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
