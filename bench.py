@@ -50,6 +50,17 @@ WORKLOAD = ("BASELINE configs[1]: DINOv2-B/14 detector (reference default ctor: 
             "deformable decoder, 50 queries, 91 classes) inference at 518x518, 1370 tokens/image")
 
 
+def _ncu_traffic():
+    """DRAM bytes per GEMM launch (read + write) from the committed `ncu --set full` capture of one
+    encoder layer (profiles/): average over its four GEMMs; None if the summary is not there."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_final2_traffic.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh)["gemm"]["avg_dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def _config(world):
     return {"workload": WORKLOAD, "batch_per_gpu": BATCH, "global_batch": BATCH * world,
             "parallelism": f"dp{world}", "weights": "random-init",
@@ -302,7 +313,7 @@ def run_ours(args):
     roof = {"kernel": "dod::gemm_kernel (tcgen05/TMEM/TMA)", "bound": "tensor", "achieved": gemm_tflops,
             "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": gemm_tflops / peaks["tflops"],
             "peak_source": f"{peaks['source']} sustained bf16 (kernel timed inside a long step)",
-            "traffic": None, "launches_per_step": gl / args.steps,
+            "traffic": _ncu_traffic(), "launches_per_step": gl / args.steps,
             "share_of_step": gt / (ms_dev if world == 1 else e0.elapsed_time(e1))}
     extra = {
         "fmha": {"kernel": "dod::fmha_kernel", "bound": "tensor", "achieved": ff / (ft * 1e-3) / 1e12,
