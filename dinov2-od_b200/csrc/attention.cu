@@ -3,14 +3,18 @@
 // One CTA per (batch, head, 128-query tile).  Flash-style single pass over the
 // keys in tiles of 128:
 //     S = Q.K^T           tcgen05.mma  (SS: Q, K from 128B-swizzled smem)   -> TMEM
-//     P = exp2(S*c - m)   4 softmax warps, one query row per thread (tcgen05.ld)
+//     P = exp2(S*c - m)   8 softmax warps, two threads per query row (64 key columns each,
+//                         row maximum exchanged through shared memory), S held in registers
 //     O += P.V            tcgen05.mma  (TS: P from TMEM as bf16, V MN-major smem)
 // O stays in TMEM for the whole pass; the running max is only advanced (and O
 // rescaled through tcgen05.ld/st) when it grows by more than 2^8, so the common
-// iteration touches O not at all.  K and V are double-buffered TMA rings; the
-// S_{j+1} MMA is issued as soon as S_j has been pulled into registers so the
-// tensor pipe runs under the softmax.  Two CTAs are resident per SM (80 KB smem,
-// 256 TMEM columns each), which overlaps one CTA's softmax with the other's MMA.
+// iteration touches O not at all.  K and V are double-buffered TMA rings fed by two
+// single-thread issue warps (Q/K loads + Q.K^T, V loads + P.V); the S_{j+1} MMA is
+// issued as soon as S_j has been pulled into registers so the tensor pipe runs under
+// the softmax.  Two CTAs are resident per SM (87 KB smem, 256 TMEM columns each).
+// The kernel is bound by the XU pipe (16 ex2/clk/SM): see profiles/r01_summary.md for
+// the measured phase timeline and the variants that were tried and dropped.
+// Optionally writes the per-row log-sum-exp consumed by dod_fmha_bwd.
 //
 // Replaces F.scaled_dot_product_attention behind HF Dinov2SelfAttention
 // (transformers modeling_dinov2.py:215-229); scale 1/sqrt(64), non-causal,
@@ -44,28 +48,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-// exp2 on the FMA pipe (Cody-Waite + degree-3 minimax, rel. error 7.5e-5 -- P is rounded to bf16
-// right after, ulp 2^-9): x = n + f with n = rint(x), f in [-0.5, 0.5]; 2^f by Horner; n is added to
-// the exponent field with one shift-add.  Two elements per packed f32x2 instruction.  The MUFU unit
-// (16 ex2/clk/SM) is the bottleneck of the softmax at head dim 64 -- 128 ex2 per row and tile against
-// 512 tensor-pipe cycles -- so a fixed fraction of every row (kPolyMask) is evaluated here instead.
-__device__ __forceinline__ float2 exp2_poly_x2(float2 x) {
-  x.x = fmaxf(x.x, -125.0f);
-  x.y = fmaxf(x.y, -125.0f);
-  const float2 magic = make_float2(12582912.0f, 12582912.0f);  // 1.5 * 2^23
-  const float2 t = __fadd2_rn(x, magic);
-  const float2 n = __fadd2_rn(t, make_float2(-12582912.0f, -12582912.0f));
-  const float2 f = __fadd2_rn(x, make_float2(-n.x, -n.y));
-  float2 q = __ffma2_rn(f, make_float2(5.517166722e-02f, 5.517166722e-02f),
-                        make_float2(2.426111221e-01f, 2.426111221e-01f));
-  q = __ffma2_rn(q, f, make_float2(6.932609858e-01f, 6.932609858e-01f));
-  q = __ffma2_rn(q, f, make_float2(9.999280736e-01f, 9.999280736e-01f));
-  float2 r;
-  r.x = __int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23));
-  r.y = __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23));
-  return r;
-}
-
 #ifdef DOD_FMHA_TRACE
 // developer instrumentation (tools/build_variant.sh trace attention.cu -DDOD_FMHA_TRACE): SM-clock
 // stamps at the hand-off points of one CTA, read back with dod_debug_fmha_trace()
@@ -97,8 +79,6 @@ __device__ __forceinline__ void pair_sync(int quad) {
   asm volatile("bar.sync %0, 64;" ::"r"(quad + 1) : "memory");
 }
 
-// kPolyMask: which pairs (index mod 8) of a row take the polynomial exp2 path
-template <uint32_t kPolyMask>
 __global__ void __launch_bounds__(kThreads, 2)
 fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -253,57 +233,31 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
       s_ready = false;
       TRACE(half, j, 1, 0);
       const int valid = p.seq - j * kTile - half * 64;  // keys valid in this thread's 64 columns
-      // kPolyMask == 0 (default): S is read from TMEM once and held in 64 registers.  The polynomial
-      // variants need more live registers than the 96 available with 2 CTAs/SM, so they read S twice
-      // (row maximum, then exponentials), 32 columns at a time.
-      constexpr bool kSinglePass = kPolyMask == 0 || kPolyMask >= 0x100;
-      constexpr bool kProbeNoLoad = kPolyMask == 0x200;  // timing experiment: skip the TMEM read of S
-      uint32_t sraw[kSinglePass ? 2 : 1][32];
-      float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t(&v)[32] = sraw[kSinglePass ? c : 0];
-        if (!kProbeNoLoad) tmem_ld_32x32(t_lane + kColS + half * 64 + c * 32, v);
-        else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(float(row + i + j) * 1e-3f);
-        }
-        if (!kSinglePass || c == 1) tmem_ld_wait();
-        if (kSinglePass && c == 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(s_free);  // S_j is in registers: the next Q.K^T may overwrite it
-        }
-        if (!kSinglePass) {
-          if (valid < 64) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i >= valid) v[i] = 0xff800000u;
-          }
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            mx0 = fmaxf(mx0, __uint_as_float(v[i]));
-            mx1 = fmaxf(mx1, __uint_as_float(v[i + 1]));
-          }
-        }
-      }
-      if (kSinglePass) {
-        if (valid < 64) {
-          // tail tile only (1370 = 10*128 + 90): keys beyond the sequence get -inf
-#pragma unroll
-          for (int c = 0; c < 2; ++c)
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i >= valid) sraw[kSinglePass ? c : 0][i] = 0xff800000u;
-        }
+      // S is read from TMEM once and held in 64 registers (two-pass and polynomial-exp2 variants were
+      // measured slower: profiles/r01_summary.md)
+      uint32_t sraw[2][32];
+      tmem_ld_32x32(t_lane + kColS + half * 64, sraw[0]);
+      tmem_ld_32x32(t_lane + kColS + half * 64 + 32, sraw[1]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free);  // S_j is in registers: the next Q.K^T may overwrite it
+      if (valid < 64) {
+        // tail tile only (1370 = 10*128 + 90): keys beyond the sequence get -inf
 #pragma unroll
         for (int c = 0; c < 2; ++c)
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            mx0 = fmaxf(mx0, __uint_as_float(sraw[kSinglePass ? c : 0][i]));
-            mx1 = fmaxf(mx1, __uint_as_float(sraw[kSinglePass ? c : 0][i + 1]));
-          }
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= valid) sraw[c][i] = 0xff800000u;
       }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          mx0 = fmaxf(mx0, __uint_as_float(sraw[c][i]));
+          mx1 = fmaxf(mx1, __uint_as_float(sraw[c][i + 1]));
+        }
       // row maximum over both halves: exchange through shared memory (double buffered by parity)
       float* xm = xmax + (j & 1) * 2 * kTile;
       TRACE(half, j, 2, __float_as_uint(fmaxf(mx0, mx1)));
@@ -325,32 +279,12 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
       const float2 nm2 = make_float2(-m_used, -m_used);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        uint32_t(&v)[32] = sraw[kSinglePass ? c : 0];
-        if (!kSinglePass) {
-          tmem_ld_32x32(t_lane + kColS + half * 64 + c * 32, v);
-          tmem_ld_wait();
-          if (c == 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(s_free);  // S_j fully consumed: the next Q.K^T may overwrite it
-          }
-          if (valid < 64) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i >= valid) v[i] = 0xff800000u;
-          }
-        }
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const int pi = c * 16 + (i >> 1);  // pair index 0..31
-          const float2 x =
-              __ffma2_rn(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, nm2);
-          float2 e;
-          if (kPolyMask == 0x100) e = make_float2(fminf(x.x, 1.0f), fminf(x.y, 1.0f));  // timing experiment: no MUFU
-          else if ((kPolyMask >> (pi & 7)) & 1) e = exp2_poly_x2(x);
-          else e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(sraw[c][i]), __uint_as_float(sraw[c][i + 1])), sc2, nm2);
+          const float2 e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
           sum2 = __fadd2_rn(sum2, e);
-          pk[pi] = pack_bf16x2(e.x, e.y);
+          pk[c * 16 + (i >> 1)] = pack_bf16x2(e.x, e.y);
         }
         if (c == 0) {
           if (j > 0) o_ready = mbar_test_wait(o_full, (j - 1) & 1);
@@ -443,17 +377,10 @@ extern "C" int32_t dod_fmha_fwd(const dod_fmha_args* a, dod_stream_t stream_) {
   DOD_REQUIRE(a->q_off + a->heads * kD <= a->ld && a->k_off + a->heads * kD <= a->ld &&
                   a->v_off + a->heads * kD <= a->ld && a->heads * kD <= a->ldo,
               "dod_fmha_fwd: head slices exceed the row");
-  // DOD_FMHA_POLY selects how many of every 8 exp2 pairs run on the FMA pipe (0, 2, 3 or 4)
-  static int poly = -1;
-  if (poly < 0) {
-    const char* e = getenv("DOD_FMHA_POLY");
-    poly = e ? atoi(e) : 0;  // measured best on B200: MUFU only (profiles/r01_summary.md)
-    DOD_CUDA_OK(cudaFuncSetAttribute(fmha_kernel<0x00>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    DOD_CUDA_OK(cudaFuncSetAttribute(fmha_kernel<0x12>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    DOD_CUDA_OK(cudaFuncSetAttribute(fmha_kernel<0x52>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    DOD_CUDA_OK(cudaFuncSetAttribute(fmha_kernel<0x5a>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    DOD_CUDA_OK(cudaFuncSetAttribute(fmha_kernel<0x100>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    DOD_CUDA_OK(cudaFuncSetAttribute(fmha_kernel<0x200>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  static bool attr_set = false;
+  if (!attr_set) {
+    DOD_CUDA_OK(cudaFuncSetAttribute(fmha_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
   }
   CUtensorMap tm;
   if (int rc = make_tmap_3d(&tm, a->qkv, 2, a->batch, a->seq, a->ld, a->seq * a->ld, a->ld, kTile, kD))
@@ -469,12 +396,7 @@ extern "C" int32_t dod_fmha_fwd(const dod_fmha_args* a, dod_stream_t stream_) {
   p.ldo = a->ldo;
   p.lse = a->lse;
   dim3 grid((a->seq + kTile - 1) / kTile, a->heads, a->batch);
-  if (poly == 0) fmha_kernel<0x00><<<grid, kThreads, kSmemBytes, stream>>>(tm, p);
-  else if (poly == 2) fmha_kernel<0x12><<<grid, kThreads, kSmemBytes, stream>>>(tm, p);
-  else if (poly == 4) fmha_kernel<0x5a><<<grid, kThreads, kSmemBytes, stream>>>(tm, p);
-  else if (poly == 9) fmha_kernel<0x100><<<grid, kThreads, kSmemBytes, stream>>>(tm, p);  // no-exp timing probe
-  else if (poly == 8) fmha_kernel<0x200><<<grid, kThreads, kSmemBytes, stream>>>(tm, p);  // no-S-load timing probe
-  else fmha_kernel<0x52><<<grid, kThreads, kSmemBytes, stream>>>(tm, p);
+  fmha_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tm, p);
   int rc = check_cuda(cudaGetLastError(), "fmha_kernel launch");
   if (rc == 0) count_launch();
   return rc;

@@ -1,4 +1,4 @@
-"""Developer probe: time the attention kernel alone (B/14 shapes) for DOD_FMHA_POLY variants."""
+"""Developer probe: time the attention kernel alone (B/14 shapes) on the bench shape."""
 import os, sys, torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dinov2-od_b200"))
 from dino_detector import ops
@@ -14,4 +14,4 @@ for _ in range(10):
     ops.fmha(qkv, b, s, h, q_off=0, k_off=d, v_off=2 * d, scale=0.125)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
-print(f"qtiles={os.environ.get('DOD_FMHA_QTILES','-')} poly={os.environ.get('DOD_FMHA_POLY','0')} {ms*1e3:.1f} us  {4*b*h*s*s*64/ms/1e9:.0f} TFLOP/s-eq")
+print(f"fmha B/14 batch 64: {ms*1e3:.1f} us  {4*b*h*s*s*64/ms/1e9:.0f} TFLOP/s-eq")
