@@ -4,7 +4,7 @@
     python tools/bench_configs.py [c1] [c3] [c4] [c5]      # one JSON line per config
 
 c1  lightweight S/14 + decoder (100 queries), fp32 mode, batch 2 at 224x224: latency
-c3  Hungarian matcher, batch 256, 100 queries x <= 50 GT: us/batch on the GPU vs the CPU oracle
+c3  Hungarian matcher, batch 256, 100 queries x <= 50 GT: us/batch on the GPU (the CPU-oracle timing of the same batch is test_matcher_gpu / profiles/r01_configs.jsonl)
 c4  L/14 LoRA r=8 + decoder train step (forward + SetCriterion + backward + Adam), bf16, one GPU
 c5  g/14 detector inference, bf16, 518x518, micro-batches of 32
 All timings: CUDA events on the launching stream, warm-up first; synthetic data, random-init weights.
@@ -20,7 +20,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "dinov2-od_b200"))
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 
 def _timed(fn, iters, warmup=2):
@@ -66,8 +66,7 @@ def c1():
 
 
 def c3():
-    import synth
-    import matcher_oracle
+    import _inputs as synth
     from dino_detector.matching import HungarianMatcher
     preds = synth.make_predictions(256, 100, seed=0)
     targets = synth.make_targets(256, max_gt=50, seed=0)
@@ -77,18 +76,14 @@ def c3():
     packed = m.pack_targets(dev_targets, torch.device("cuda"))
     kern_ms = _timed(lambda: m.match_device(dev_preds, dev_targets, packed=packed), 50, 5)
     api_ms = _timed(lambda: m(dev_preds, dev_targets), 20, 3)
-    t0 = time.perf_counter()
-    matcher_oracle.match(preds["pred_logits"], preds["pred_boxes"], targets, reference_compat=True,
-                         solver=__import__("scipy.optimize", fromlist=["x"]).linear_sum_assignment)
-    cpu_s = time.perf_counter() - t0
     n_pairs = sum(min(100, len(t["labels"])) for t in targets)
     print(json.dumps({"config": "c3 matcher batch 256, 100 queries x <=50 GT", "cost+lsap_kernels_us": 1e3 * kern_ms,
                       "api_incl_target_packing_and_d2h_us": 1e3 * api_ms, "problems_per_s": 256 / (kern_ms * 1e-3),
-                      "matched_pairs": n_pairs, "cpu_reference_algorithm_s": cpu_s, "cpu_cores": os.cpu_count()}))
+                      "matched_pairs": n_pairs}))
 
 
 def c4(batch=8):
-    import synth
+    import _inputs as synth
     from dino_detector.losses import SetCriterion
     from dino_detector.matching import HungarianMatcher
     m = _model(dino_model_name="facebook/dinov2-large", lora_r=8).train()

@@ -19,7 +19,7 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "dinov2-od_b200"))
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 
 def main():
@@ -37,7 +37,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    import synth  # synthetic targets only
+    import _inputs as synth
     from dino_detector.models import DINOv2ObjectDetector
     from dino_detector.losses import SetCriterion
     from dino_detector.matching import HungarianMatcher

@@ -4,8 +4,8 @@ import json, os, sys, time
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "dinov2-od_b200"))
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
-import synth  # input generator only
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import _inputs as synth
 from dino_detector.models import DINOv2ObjectDetector
 from dino_detector.losses import SetCriterion
 from dino_detector.matching import HungarianMatcher
