@@ -119,6 +119,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// One lane of a converged warp (elect.sync).  The MMA-issuing warps of the GEMM keep all 32 lanes on a
+// uniform control path and elect only the tcgen05 instructions: the descriptors then live in uniform
+// registers and the four UTCHMMA of a k-block issue back to back (an `if (lane == 0) { loop }` region
+// made ptxas rebuild them through ELECT / R2UR sequences, ~17 dependent instructions per MMA).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // Non-blocking phase test (no hardware sleep): lets a warp look at a barrier early, under work it
 // has to do anyway, and skip the ~100-cycle wait instruction later if the phase already completed.
 __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {

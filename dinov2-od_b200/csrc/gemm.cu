@@ -7,7 +7,8 @@
 //     both operands are TMA-loaded as [rows x 64] bf16 boxes with the 128-byte
 //     swizzle and consumed by tcgen05.mma straight from shared memory.
 //   * CTA tile 128 x BN (BN = 256 / 128 / 64), BK = 64; 3..6 smem stages.
-//   * warp 0: TMA producer, warp 1: MMA issuer (one lane), warps 2..9: epilogue.
+//   * warp 0: TMA producer (one lane), warp 1: MMA issuer (converged warp, elected
+//     tcgen05 instructions), warps 2..9: epilogue.
 //   * two TMEM accumulator stages, so the epilogue of tile i overlaps the
 //     mainloop of tile i+1; grid = min(tiles, #SM) persistent CTAs; tiles are
 //     walked N-fastest so CTAs running together share A rows through L2.
@@ -248,6 +249,11 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
         r[4 * j] += q.x; r[4 * j + 1] += q.y; r[4 * j + 2] += q.z; r[4 * j + 3] += q.w;
       }
     }
+    // Nothing to store (chunk past N, or this warp's rows past M): leave the staging buffers alone.
+    // Rotating them without committing a store let a later chunk overwrite a buffer whose TMA store
+    // was still in flight (wait_group.read<1> only covers COMMITTED groups): the last valid chunk of a
+    // mostly-empty N tile was then written as zeros.
+    if (!in_range || row0 >= p.M) continue;
     // the store issued two chunks ago read this buffer: wait until it has been drained
     if (lane == 0) tma_store_wait_read<1>();
     __syncwarp();
@@ -271,7 +277,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
     }
     fence_proxy_async_smem();
     __syncwarp();
-    if (lane == 0 && in_range && row0 < p.M) {
+    if (lane == 0) {
       tma_store_4d(tm_out, ob, n0, row0, bz % p.batch_inner, bz / p.batch_inner);
       tma_store_commit();
     }
@@ -462,8 +468,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp converged, tcgen05 instructions elected) ==========
+    {
       const bool at = TRANS && p.a_trans != 0, wt = TRANS && p.w_trans != 0;
       const uint32_t idesc = make_idesc_bf16(BM, BN, at, wt);
       const uint32_t a_lbo = at ? kMnBlockBytes : 16, b_lbo = wt ? kMnBlockBytes : 16;
@@ -485,13 +491,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
           const uint32_t sb = sa + L::kStageA;
           const uint64_t da = make_sdesc_sw128(sa, a_lbo, 1024);
           const uint64_t db = make_sdesc_sw128(sb, b_lbo, 1024);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // K-major: advance 16 bf16 = 32 B inside the 128-B swizzle row: +2 in (addr >> 4)
-            umma_ss(d_tmem, da + a_step * k, db + b_step * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              // K-major: advance 16 bf16 = 32 B inside the 128-B swizzle row: +2 in (addr >> 4)
+              umma_ss(d_tmem, da + a_step * k, db + b_step * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty[s]);  // frees the smem stage when these MMAs retire
+            if (kb == kblocks - 1) umma_commit(&tfull[acc]);
           }
-          umma_commit(&empty[s]);  // frees the smem stage when these MMAs retire
-          if (kb == kblocks - 1) umma_commit(&tfull[acc]);
+          __syncwarp();
           if (++s == kStages) { s = 0; ph ^= 1; }
         }
       }
@@ -661,8 +670,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && rank == 0) {
+    // ===================== MMA issuer (leader CTA only; whole warp converged, tcgen05 elected) ======
+    if (rank == 0) {
       const bool at = TRANS && p.a_trans != 0, wt = TRANS && p.w_trans != 0;
       const uint32_t idesc = make_idesc_bf16(256, BN, at, wt);
       const uint32_t a_lbo = at ? kMnBlockBytes : 16, b_lbo = wt ? kMnBlockBytes : 16;
@@ -683,11 +692,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
           const uint32_t sb = sa + L::kStageA;
           const uint64_t da = make_sdesc_sw128(sa, a_lbo, 1024);
           const uint64_t db = make_sdesc_sw128(sb, b_lbo, 1024);
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_ss_2sm(d_tmem, da + a_step * k, db + b_step * k, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit_2sm(&empty[s], 3);  // frees the stage in BOTH CTAs
-          if (kb == kblocks - 1) umma_commit_2sm(&tfull[acc], 3);
+            for (int k = 0; k < BK / 16; ++k)
+              umma_ss_2sm(d_tmem, da + a_step * k, db + b_step * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_2sm(&empty[s], 3);  // frees the stage in BOTH CTAs
+            if (kb == kblocks - 1) umma_commit_2sm(&tfull[acc], 3);
+          }
+          __syncwarp();
           if (++s == kStages) { s = 0; ph ^= 1; }
         }
       }

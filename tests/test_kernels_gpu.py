@@ -34,7 +34,7 @@ def _randn(shape, g, scale=1.0):
 @pytest.mark.parametrize("m,n,k", [
     (128, 64, 64), (128, 128, 128), (256, 256, 256), (300, 768, 768), (1000, 2304, 768),
     (87, 96, 392), (2740, 3072, 768), (513, 56, 768), (4096, 768, 3072), (129, 8, 64),
-    (5000, 1024, 592),
+    (5000, 1024, 592), (4700, 520, 200), (20000, 520, 136), (16600, 256, 72),
 ])
 def test_gemm_plain(ops, m, n, k):
     g = _gen(m * 7 + n * 3 + k)
@@ -49,7 +49,26 @@ def test_gemm_plain(ops, m, n, k):
     assert _rel(out_b, ref) < 1e-2
 
 
-@pytest.mark.parametrize("m", [300, 777, 2049])
+@pytest.mark.parametrize("n,k,res", [(2304, 768, False), (768, 3072, True)])
+def test_gemm_bench_shapes_full_size(ops, n, k, res):
+    """The bench workload's own GEMM shapes (64 images x 1370 tokens = 87 680 rows, 41 tiles per CTA pair):
+    every output element against an fp32 product of the same bf16 operands."""
+    m = 64 * 1370
+    g = _gen(n + k)
+    a = _randn((m, k), g).bfloat16()
+    w = _randn((n, k), g, 1 / math.sqrt(k)).bfloat16()
+    bias = _randn((n,), g)
+    ref = a.float() @ w.float().t() + bias
+    if res:
+        scale, r = _randn((n,), g), _randn((m, n), g)
+        out = ops.gemm(a, w, bias, scale=scale, residual=r, out_dtype=torch.float32)
+        assert _rel(out, r + scale * ref) < 2e-5
+    else:
+        assert _rel(ops.gemm(a, w, bias, out_dtype=torch.float32), ref) < 2e-5
+        assert _rel(ops.gemm(a, w, bias), ref) < 1e-2
+
+
+@pytest.mark.parametrize("m", [300, 777, 2049, 4700, 17000])
 @pytest.mark.parametrize("act", ["gelu", "relu"])
 def test_gemm_act_scale_residual(ops, act, m):
     n, k = 384, 320
