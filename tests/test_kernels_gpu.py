@@ -199,6 +199,23 @@ def test_fmha(ops, b, s, h):
     assert (out.float() - ref).abs().max().item() < 2e-2
 
 
+def test_fmha_bench_shape_full_size(ops):
+    """The bench workload's attention (64 images x 12 heads x 1370 tokens, 8448 CTAs): every (image, head)
+    against torch SDPA on the same bf16 inputs, and a few slices against an fp32 softmax."""
+    b, s, h = 64, 1370, 12
+    d = h * 64
+    g = _gen(5)
+    qkv = _randn((b * s, 3 * d), g, 0.7).bfloat16()
+    out = ops.fmha(qkv, b, s, h, q_off=0, k_off=d, v_off=2 * d, scale=0.125).view(b, s, h, 64)
+    q, k, v = qkv.view(b, s, 3, h, 64).permute(2, 0, 3, 1, 4)
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3)     # bf16 library path
+    assert (out.float() - ref.float()).abs().max().item() < 2e-2
+    for bi, hi in [(0, 0), (17, 5), (63, 11)]:
+        qf, kf, vf = (t[bi, hi].float() for t in (q, k, v))
+        exact = torch.softmax(qf @ kf.t() * 0.125, dim=-1) @ vf
+        assert (out[bi, :, hi].float() - exact).abs().max().item() < 1e-2
+
+
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32])
 @pytest.mark.parametrize("b,lq,lk,h,dh", [(2, 50, 50, 8, 96), (3, 100, 257, 4, 64), (1, 25, 1370, 8, 96),
                                           (2, 17, 33, 4, 192), (1, 100, 100, 8, 96), (2, 128, 128, 4, 64)])
