@@ -284,6 +284,118 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
   }
 }
 
+// Residual epilogue of the CTA-pair kernel (fp32 output, BN = 256): the fp32 residual is the larger HBM
+// stream of the K = 768 projection GEMM, and one 2 KB chunk in flight per warp (16 KB per SM) did not
+// cover DRAM latency (proj ran at 4.1 TB/s of HBM traffic).  Each warp therefore runs a ring of
+// kResRing chunk buffers that is used IN PLACE: TMA load of the residual chunk -> add accumulator ->
+// written back to the same swizzled buffer -> TMA store from it.  The load for chunk k + kResRing - 1 is
+// issued when chunk k has been stored, into the buffer of chunk k - 1 once its store has been read, and
+// the stream of chunks continues ACROSS the warp's tiles, so kResRing - 1 chunks (6 KB per warp, 48 KB
+// per SM) are always in flight, also while the warp waits for the next accumulator.
+constexpr int kResRing = 4;
+
+struct ResStream {
+  const CUtensorMap* tm;
+  uint8_t* buf;    // kResRing chunk buffers of this warp
+  uint64_t* bars;  // kResRing full barriers of this warp
+  int tile, c, num_tiles, num_pairs, tiles_n, rank, half;
+  int row0, col_base;
+  uint32_t issued;
+
+  __device__ __forceinline__ void locate(int quad) {
+    row0 = ((tile / tiles_n) * 2 + rank) * BM + quad * 32;
+    col_base = (tile % tiles_n) * 256;
+  }
+  // whole warp calls; lane 0 issues the load of the next chunk of the stream
+  __device__ __forceinline__ void issue(int lane, int quad) {
+    if (tile >= num_tiles) return;
+    if (lane == 0) {
+      const uint32_t slot = issued % kResRing;
+      mbar_expect_tx(&bars[slot], kChunkBytes);
+      tma_load_2d(buf + slot * kChunkBytes, tm, &bars[slot], col_base + c * 16, row0);
+    }
+    ++issued;
+    c += 2;
+    if (c >= 16) {
+      c = half;
+      tile += num_pairs;
+      locate(quad);
+    }
+  }
+};
+
+__device__ __forceinline__ void epilogue_tile_res_ring(const GemmParams& p, const CUtensorMap* tm_out,
+                                                       uint32_t t_row, int mb, int nb, int quad, int half,
+                                                       int lane, ResStream& rs, uint32_t& res_wait,
+                                                       uint32_t tempty_addr) {
+  constexpr int COLS = 16, NCH = 256 / COLS;
+  const int row0 = mb * BM + quad * 32;
+#pragma unroll 1
+  for (int c = half; c < NCH; c += 2) {
+    const int n0 = nb * 256 + c * COLS;
+    uint32_t v[COLS];
+    tmem_ld_32x16(t_row + c * COLS, v);
+    tmem_ld_wait();
+    if (c + 2 >= NCH) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_addr);
+    }
+    float r[COLS];
+#pragma unroll
+    for (int j = 0; j < COLS; ++j) r[j] = __uint_as_float(v[j]);
+    const bool in_range = n0 < p.N;
+    if (in_range) {
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < COLS; j += 4) {
+          if (n0 + j < p.N) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+            r[j] += b.x; r[j + 1] += b.y; r[j + 2] += b.z; r[j + 3] += b.w;
+          }
+        }
+      }
+      if (p.act == DOD_ACT_GELU_ERF) {
+#pragma unroll
+        for (int j = 0; j < COLS; ++j) r[j] = gelu_erf(r[j]);
+      } else if (p.act == DOD_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < COLS; ++j) r[j] = fmaxf(r[j], 0.0f);
+      }
+      if (p.scale) {
+#pragma unroll
+        for (int j = 0; j < COLS; j += 4) {
+          if (n0 + j < p.N) {
+            const float4 s = __ldg(reinterpret_cast<const float4*>(p.scale + n0 + j));
+            r[j] *= s.x; r[j + 1] *= s.y; r[j + 2] *= s.z; r[j + 3] *= s.w;
+          }
+        }
+      }
+    }
+    const uint32_t slot = res_wait % kResRing;
+    mbar_wait(&rs.bars[slot], (res_wait / kResRing) & 1);
+    ++res_wait;
+    uint8_t* rb = rs.buf + slot * kChunkBytes;
+    // every lane reads and rewrites only its own row of the buffer: no cross-lane hazard
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float4* q = reinterpret_cast<float4*>(rb + sw64(lane, j));
+      const float4 x = *q;
+      *q = make_float4(r[4 * j] + x.x, r[4 * j + 1] + x.y, r[4 * j + 2] + x.z, r[4 * j + 3] + x.w);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      if (in_range && row0 < p.M) tma_store_4d(tm_out, rb, n0, row0, 0, 0);
+      tma_store_commit();  // one group per chunk (possibly empty) keeps the wait_group arithmetic uniform
+      // the next load goes into the buffer of the PREVIOUS chunk: its store must have been read
+      tma_store_wait_read<1>();
+    }
+    __syncwarp();
+    rs.issue(lane, quad);
+  }
+}
+
 // Register -> global epilogue (one row per thread).  Kept for the patch-embedding row map.
 template <int BN>
 __device__ __forceinline__ void epilogue_tile_direct(const GemmParams& p, uint32_t t_row, int mb,
@@ -564,9 +676,11 @@ struct SmemLayout2 {
   static constexpr int kStageB = 128 * BK * 2;  // this CTA's half of the 256 W rows
   static constexpr int kStage = kStageA + kStageB;
   static constexpr int kStages = RES ? 5 : 6;
-  static constexpr int kEpiBufs = RES ? 4 : 2;
+  static constexpr int kEpiBufs = RES ? kResRing : 2;  // per warp: residual ring used in place, or 2 out
+  static constexpr int kResBars = RES ? kResRing : 2;   // per warp
   static constexpr int kEpiBytes = kEpiWarps * kEpiBufs * kChunkBytes;
   static constexpr int kBarBytes = 512;
+  static_assert((2 * (RES ? 5 : 6) + 4 + kEpiWarps * kResBars) * 8 + 4 <= kBarBytes, "barrier area");
   static constexpr int kTotal = kStages * kStage + kEpiBytes + kBarBytes + 1024;
   static_assert(kTotal <= 232448, "shared memory budget exceeded");
 };
@@ -592,8 +706,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
   uint64_t* empty = bars + kStages;             // [kStages]  one per CTA (multicast commit)
   uint64_t* tfull = bars + 2 * kStages;         // [2]        one per CTA (multicast commit)
   uint64_t* tempty = bars + 2 * kStages + 2;    // [2]        leader only, 2 x kEpiWarps arrivals
-  uint64_t* res_bars = bars + 2 * kStages + 4;  // [kEpiWarps][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bars + 2 * kEpiWarps);
+  uint64_t* res_bars = bars + 2 * kStages + 4;  // [kEpiWarps][kResBars]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bars + L::kResBars * kEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -618,7 +732,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
       mbar_init(&tfull[s], 1);
       mbar_init(&tempty[s], 2 * kEpiWarps);
     }
-    for (int s = 0; s < 2 * kEpiWarps; ++s) mbar_init(&res_bars[s], 1);
+    for (int s = 0; s < L::kResBars * kEpiWarps; ++s) mbar_init(&res_bars[s], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_2sm<kTmemCols>(tmem_slot);
@@ -710,10 +824,27 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     const int half = (warp - 2) >> 2;
     const int ew = warp - 2;
     uint8_t* out_buf = epi_base + ew * L::kEpiBufs * kChunkBytes;
-    uint8_t* res_buf = out_buf + 2 * kChunkBytes;
-    uint64_t* res_full = res_bars + 2 * ew;
+    uint64_t* res_full = res_bars + L::kResBars * ew;
     uint32_t out_cnt = 0, res_issue = 0, res_wait = 0;
     const uint32_t tempty_leader[2] = {map_to_cta(&tempty[0], 0), map_to_cta(&tempty[1], 0)};
+    ResStream rs;
+    if constexpr (RES) {
+      // launch_bn sends residual problems here only with fp32 output and batch == 1
+      rs.tm = &tm_res;
+      rs.buf = out_buf;
+      rs.bars = res_full;
+      rs.tile = pair;
+      rs.c = half;
+      rs.num_tiles = num_tiles;
+      rs.num_pairs = num_pairs;
+      rs.tiles_n = p.tiles_n;
+      rs.rank = int(rank);
+      rs.half = half;
+      rs.issued = 0;
+      rs.locate(quad);
+#pragma unroll
+      for (int i = 0; i < kResRing - 1; ++i) rs.issue(lane, quad);
+    }
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
       const int bz = tile / tiles_per_batch, tl = tile % tiles_per_batch;
@@ -724,12 +855,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
       mbar_wait(&tfull[acc], acc_ph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
-      if (p.out_f32) {
-        epilogue_tile_tma<BN, RES, true>(p, &tm_out, &tm_res, t_row, bz, mb, nb, quad, half, lane, out_buf,
-                                         res_buf, res_full, out_cnt, res_issue, res_wait, tempty_leader[acc]);
+      if constexpr (RES) {
+        epilogue_tile_res_ring(p, &tm_out, t_row, mb, nb, quad, half, lane, rs, res_wait, tempty_leader[acc]);
+      } else if (p.out_f32) {
+        epilogue_tile_tma<BN, false, true>(p, &tm_out, &tm_res, t_row, bz, mb, nb, quad, half, lane, out_buf,
+                                           out_buf, res_full, out_cnt, res_issue, res_wait, tempty_leader[acc]);
       } else {
         epilogue_tile_tma<BN, false, false>(p, &tm_out, &tm_res, t_row, bz, mb, nb, quad, half, lane,
-                                            out_buf, res_buf, res_full, out_cnt, res_issue, res_wait,
+                                            out_buf, out_buf, res_full, out_cnt, res_issue, res_wait,
                                             tempty_leader[acc]);
       }
     }
