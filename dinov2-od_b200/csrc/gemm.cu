@@ -58,7 +58,21 @@ struct GemmParams {
   int patch_rows;
   int direct;  // 1: register -> global epilogue (patch rows / shapes TMA cannot store)
   int a_trans, w_trans;  // operand stored [K, M] / [K, N]: MN-major smem tiles (64-column blocks 8 KB apart)
+  // LayerNorm folded across two GEMMs (include/dod.h): producer outputs / consumer inputs
+  __nv_bfloat16* out2;
+  int64_t ldo2;
+  float* stats_out;
+  const float* row_scale;  // consumer: f32 [M], accumulator of row m is multiplied by it before bias / act
 };
+
+// consumer side of the folded LayerNorm: rstd of this thread's row.  Requested one TILE ahead: the fc1 GEMM
+// is epilogue-bound, so a load issued at the start of a tile's epilogue is an L2 round trip (~1000 clk) on the
+// critical path of every tile (ncu: long-scoreboard stalls +40 %, fc1 +14 %)
+__device__ __forceinline__ float load_row_scale(const GemmParams& p, int row) {
+  float v = 0.0f;
+  if (row < p.M) asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p.row_scale + row));
+  return v;
+}
 
 // MN-major operand tile in shared memory: [MN / 64 blocks][64 K rows][64 MN elements = 128 B],
 // 128B-swizzled; one TMA box per block.  tcgen05 descriptor: LBO = 8192 (between 64-wide MN blocks),
@@ -143,7 +157,8 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
                                                   uint8_t* out_buf, uint8_t* res_buf,
                                                   uint64_t* res_full, uint32_t& out_cnt,
                                                   uint32_t& res_issue, uint32_t& res_wait,
-                                                  uint32_t tempty_addr) {
+                                                  uint32_t tempty_addr, uint64_t* tfull_bar,
+                                                  uint32_t tfull_phase, float ln_rstd = 0.0f) {
   constexpr int COLS = OUT_F32 ? 16 : 32;
   const bool swiglu = p.act == DOD_ACT_SWIGLU;
   const int width = swiglu ? BN / 2 : BN;  // output columns of this tile
@@ -151,7 +166,6 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
   const int row0 = mb * BM + quad * 32;
   const int col_base = nb * width;
   const int n_out = swiglu ? p.N / 2 : p.N;
-
   if constexpr (RES) {
     if (half < nch) {
       if (lane == 0) {
@@ -162,6 +176,10 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
       ++res_issue;
     }
   }
+
+  // the accumulator is awaited HERE, after the caller requested the row statistics of the folded LayerNorm
+  mbar_wait(tfull_bar, tfull_phase);
+  tc_fence_after();
 
 #pragma unroll 1
   for (int c = half; c < nch; c += 2) {
@@ -197,6 +215,10 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
 #pragma unroll
       for (int j = 0; j < COLS; ++j) {
         float gv = r[j], uv = __uint_as_float(u[j]);
+        if (p.row_scale) {
+          gv *= ln_rstd;
+          uv *= ln_rstd;
+        }
         if (p.bias) {
           gv += __ldg(p.bias + nw + j);
           uv += __ldg(p.bias + nw + BN / 2 + j);
@@ -204,7 +226,19 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
         r[j] = silu(gv) * uv;
       }
     } else if (in_range) {
-      if (p.bias) {
+      if (p.row_scale) {
+        // folded LayerNorm: the rows of W'' sum to zero, so acc is already (h - mean) . (gamma W)^T
+#pragma unroll
+        for (int j = 0; j < COLS; j += 4) {
+          if (n0 + j < p.N) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+            r[j] = fmaf(r[j], ln_rstd, b.x);
+            r[j + 1] = fmaf(r[j + 1], ln_rstd, b.y);
+            r[j + 2] = fmaf(r[j + 2], ln_rstd, b.z);
+            r[j + 3] = fmaf(r[j + 3], ln_rstd, b.w);
+          }
+        }
+      } else if (p.bias) {
 #pragma unroll
         for (int j = 0; j < COLS; j += 4) {
           if (n0 + j < p.N) {
@@ -290,13 +324,17 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
 // kResRing chunk buffers that is used IN PLACE: TMA load of the residual chunk -> add accumulator ->
 // written back to the same swizzled buffer -> TMA store from it.  The load for chunk k + kResRing - 1 is
 // issued when chunk k has been stored, into the buffer of chunk k - 1 once its store has been read, and
-// the stream of chunks continues ACROSS the warp's tiles, so kResRing - 1 chunks (6 KB per warp, 48 KB
-// per SM) are always in flight, also while the warp waits for the next accumulator.
-constexpr int kResRing = 4;
+// the stream of chunks continues ACROSS the warp's tiles, so kResRing - 1 chunks (4 KB per warp, 32 KB
+// per SM) are always in flight, also while the warp waits for the next accumulator.  The fourth 2 KB of
+// the warp's staging area holds two 1 KB buffers for the optional bf16 copy of the output (folded
+// LayerNorm, include/dod.h), stored by TMA in the same bulk group as the fp32 chunk.
+constexpr int kResRing = 3;
+constexpr int kHalfChunkBytes = kChunkBytes / 2;  // bf16 copy of a 16-column chunk: 32 rows x 32 B
 
 struct ResStream {
   const CUtensorMap* tm;
   uint8_t* buf;    // kResRing chunk buffers of this warp
+  uint8_t* buf16;  // two half-chunk buffers (bf16 copy)
   uint64_t* bars;  // kResRing full barriers of this warp
   int tile, c, num_tiles, num_pairs, tiles_n, rank, half;
   int row0, col_base;
@@ -325,11 +363,12 @@ struct ResStream {
 };
 
 __device__ __forceinline__ void epilogue_tile_res_ring(const GemmParams& p, const CUtensorMap* tm_out,
-                                                       uint32_t t_row, int mb, int nb, int quad, int half,
+                                                       const CUtensorMap* tm_out2, uint32_t t_row, int mb, int nb, int quad, int half,
                                                        int lane, ResStream& rs, uint32_t& res_wait,
                                                        uint32_t tempty_addr) {
   constexpr int COLS = 16, NCH = 256 / COLS;
   const int row0 = mb * BM + quad * 32;
+  float st1 = 0.0f, st2 = 0.0f;  // folded LayerNorm: sums of h and h^2 over this warp's 128 columns
 #pragma unroll 1
   for (int c = half; c < NCH; c += 2) {
     const int n0 = nb * 256 + c * COLS;
@@ -381,12 +420,35 @@ __device__ __forceinline__ void epilogue_tile_res_ring(const GemmParams& p, cons
     for (int j = 0; j < 4; ++j) {
       float4* q = reinterpret_cast<float4*>(rb + sw64(lane, j));
       const float4 x = *q;
-      *q = make_float4(r[4 * j] + x.x, r[4 * j + 1] + x.y, r[4 * j + 2] + x.z, r[4 * j + 3] + x.w);
+      r[4 * j] += x.x; r[4 * j + 1] += x.y; r[4 * j + 2] += x.z; r[4 * j + 3] += x.w;
+      *q = make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+    }
+    uint8_t* hb = rs.buf16 + (res_wait & 1) * kHalfChunkBytes;
+    if (p.out2 != nullptr && in_range) {
+      // bf16 copy of the new residual stream (the next projection's A operand) + LayerNorm partial sums;
+      // 32 B per row, 32B-swizzled: 16-byte piece j of row r at r * 32 + ((j ^ ((r >> 2) & 1)) << 4)
+      if (row0 + lane < p.M) {
+#pragma unroll
+        for (int j = 0; j < COLS; ++j) {
+          st1 += r[j];
+          st2 = fmaf(r[j], r[j], st2);
+        }
+      }
+      const int sw = (lane >> 2) & 1;
+      *reinterpret_cast<uint4*>(hb + lane * 32 + (sw << 4)) =
+          make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
+                     pack_bf16x2(r[6], r[7]));
+      *reinterpret_cast<uint4*>(hb + lane * 32 + ((sw ^ 1) << 4)) =
+          make_uint4(pack_bf16x2(r[8], r[9]), pack_bf16x2(r[10], r[11]), pack_bf16x2(r[12], r[13]),
+                     pack_bf16x2(r[14], r[15]));
     }
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-      if (in_range && row0 < p.M) tma_store_4d(tm_out, rb, n0, row0, 0, 0);
+      if (in_range && row0 < p.M) {
+        tma_store_4d(tm_out, rb, n0, row0, 0, 0);
+        if (p.out2 != nullptr) tma_store_2d(tm_out2, hb, n0, row0);
+      }
       tma_store_commit();  // one group per chunk (possibly empty) keeps the wait_group arithmetic uniform
       // the next load goes into the buffer of the PREVIOUS chunk: its store must have been read
       tma_store_wait_read<1>();
@@ -394,6 +456,8 @@ __device__ __forceinline__ void epilogue_tile_res_ring(const GemmParams& p, cons
     __syncwarp();
     rs.issue(lane, quad);
   }
+  if (p.stats_out != nullptr && row0 + lane < p.M)
+    reinterpret_cast<float2*>(p.stats_out)[int64_t(nb * 2 + half) * p.M + row0 + lane] = make_float2(st1, st2);
 }
 
 // Register -> global epilogue (one row per thread).  Kept for the patch-embedding row map.
@@ -627,24 +691,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CU
     uint64_t* res_full = res_bars + 2 * ew;
     uint32_t out_cnt = 0, res_issue = 0, res_wait = 0;
     int it = 0;
+    float scale_next = 0.0f;  // row_scale of this thread's row in the NEXT tile (batch == 1 with row_scale)
+    if (p.row_scale && int(blockIdx.x) < num_tiles)
+      scale_next = load_row_scale(p, (int(blockIdx.x) / p.tiles_n) * BM + quad * 32 + lane);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int bz = tile / tiles_per_batch, tl = tile % tiles_per_batch;
       const int mb = tl / p.tiles_n, nb = tl % p.tiles_n;
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
-      mbar_wait(&tfull[acc], acc_ph);
-      tc_fence_after();
+      const float ln_rstd = scale_next;
+      if (p.row_scale && tile + int(gridDim.x) < num_tiles)
+        scale_next = load_row_scale(p, ((tile + int(gridDim.x)) / p.tiles_n) * BM + quad * 32 + lane);
       const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
       if (p.direct) {
+        mbar_wait(&tfull[acc], acc_ph);
+        tc_fence_after();
         epilogue_tile_direct<BN>(p, t_row, mb, nb, quad, half, lane, smem_u32(&tempty[acc]));
       } else if (p.out_f32) {
         epilogue_tile_tma<BN, RES, true>(p, &tm_out, &tm_res, t_row, bz, mb, nb, quad, half, lane, out_buf,
                                          res_buf, res_full, out_cnt, res_issue, res_wait,
-                                         smem_u32(&tempty[acc]));
+                                         smem_u32(&tempty[acc]), &tfull[acc], acc_ph, ln_rstd);
       } else {
         epilogue_tile_tma<BN, false, false>(p, &tm_out, &tm_res, t_row, bz, mb, nb, quad, half, lane,
                                             out_buf, res_buf, res_full, out_cnt, res_issue, res_wait,
-                                            smem_u32(&tempty[acc]));
+                                            smem_u32(&tempty[acc]), &tfull[acc], acc_ph, ln_rstd);
       }
     }
     if (lane == 0) tma_store_wait<0>();  // all bulk stores of this warp are complete
@@ -676,7 +746,8 @@ struct SmemLayout2 {
   static constexpr int kStageB = 128 * BK * 2;  // this CTA's half of the 256 W rows
   static constexpr int kStage = kStageA + kStageB;
   static constexpr int kStages = RES ? 5 : 6;
-  static constexpr int kEpiBufs = RES ? kResRing : 2;  // per warp: residual ring used in place, or 2 out
+  static constexpr int kEpiBufs = RES ? kResRing + 1 : 2;  // per warp: residual ring used in place + two
+                                                           // half-size bf16 buffers, or 2 out
   static constexpr int kResBars = RES ? kResRing : 2;   // per warp
   static constexpr int kEpiBytes = kEpiWarps * kEpiBufs * kChunkBytes;
   static constexpr int kBarBytes = 512;
@@ -690,7 +761,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
              const __grid_constant__ CUtensorMap tm_a2, const __grid_constant__ CUtensorMap tm_w2,
              const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_res,
-             const GemmParams p) {
+             const __grid_constant__ CUtensorMap tm_out2, const GemmParams p) {
   using L = SmemLayout2<RES>;
   constexpr int BN = 256;
   constexpr int kStages = L::kStages;
@@ -724,6 +795,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     }
     prefetch_tmap(&tm_out);
     if (RES) prefetch_tmap(&tm_res);
+    if (RES && p.out2 != nullptr) prefetch_tmap(&tm_out2);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -832,6 +904,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
       // launch_bn sends residual problems here only with fp32 output and batch == 1
       rs.tm = &tm_res;
       rs.buf = out_buf;
+      rs.buf16 = out_buf + kResRing * kChunkBytes;
       rs.bars = res_full;
       rs.tile = pair;
       rs.c = half;
@@ -846,24 +919,32 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
       for (int i = 0; i < kResRing - 1; ++i) rs.issue(lane, quad);
     }
     int it = 0;
+    float scale_next = 0.0f;  // row_scale of this thread's row in the NEXT tile (batch == 1 with row_scale)
+    if (!RES && p.row_scale && pair < num_tiles)
+      scale_next = load_row_scale(p, ((pair / p.tiles_n) * 2 + int(rank)) * BM + quad * 32 + lane);
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
       const int bz = tile / tiles_per_batch, tl = tile % tiles_per_batch;
       const int mb = (tl / p.tiles_n) * 2 + int(rank);  // 128-row block of THIS CTA
       const int nb = tl % p.tiles_n;
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
-      mbar_wait(&tfull[acc], acc_ph);
-      tc_fence_after();
+      const float ln_rstd = scale_next;
+      if (!RES && p.row_scale && tile + num_pairs < num_tiles)
+        scale_next = load_row_scale(p, (((tile + num_pairs) / p.tiles_n) * 2 + int(rank)) * BM + quad * 32 + lane);
       const uint32_t t_row = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
       if constexpr (RES) {
-        epilogue_tile_res_ring(p, &tm_out, t_row, mb, nb, quad, half, lane, rs, res_wait, tempty_leader[acc]);
+        mbar_wait(&tfull[acc], acc_ph);
+        tc_fence_after();
+        epilogue_tile_res_ring(p, &tm_out, &tm_out2, t_row, mb, nb, quad, half, lane, rs, res_wait,
+                               tempty_leader[acc]);
       } else if (p.out_f32) {
         epilogue_tile_tma<BN, false, true>(p, &tm_out, &tm_res, t_row, bz, mb, nb, quad, half, lane, out_buf,
-                                           out_buf, res_full, out_cnt, res_issue, res_wait, tempty_leader[acc]);
+                                           out_buf, res_full, out_cnt, res_issue, res_wait, tempty_leader[acc],
+                                           &tfull[acc], acc_ph, ln_rstd);
       } else {
         epilogue_tile_tma<BN, false, false>(p, &tm_out, &tm_res, t_row, bz, mb, nb, quad, half, lane,
                                             out_buf, out_buf, res_full, out_cnt, res_issue, res_wait,
-                                            tempty_leader[acc]);
+                                            tempty_leader[acc], &tfull[acc], acc_ph, ln_rstd);
       }
     }
     if (lane == 0) tma_store_wait<0>();
@@ -875,6 +956,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     tc_fence_after();
     tmem_dealloc_2sm<kTmemCols>(tmem_base);
   }
+}
+
+void fill_ln_params(GemmParams& p, const dod_gemm_args& a) {
+  p.out2 = reinterpret_cast<__nv_bfloat16*>(a.out_bf16);
+  p.ldo2 = a.ldo_bf16;
+  p.stats_out = a.row_stats_out;
+  p.row_scale = a.row_scale;
 }
 
 template <bool RES, bool TRANS>
@@ -910,6 +998,9 @@ int launch2(const dod_gemm_args& a, cudaStream_t stream) {
   } else {
     tm_res = tm_a;
   }
+  CUtensorMap tm_out2 = tm_a;
+  if (RES && a.out_bf16)
+    if (int rc = make_tmap_2d(&tm_out2, a.out_bf16, 2, a.m, a.n, a.ldo_bf16, 32, 16, 32)) return rc;
   GemmParams p;
   p.M = int(a.m);
   p.N = int(a.n);
@@ -931,9 +1022,11 @@ int launch2(const dod_gemm_args& a, cudaStream_t stream) {
   p.direct = 0;
   p.a_trans = a.a_trans;
   p.w_trans = a.w_trans;
+  fill_ln_params(p, a);
   const int tiles = p.tiles_m * p.tiles_n * p.batch;
   const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
-  gemm2_kernel<RES, TRANS><<<2 * pairs, kThreads, L::kTotal, stream>>>(tm_a, tm_w, tm_a2, tm_w2, tm_out, tm_res, p);
+  gemm2_kernel<RES, TRANS><<<2 * pairs, kThreads, L::kTotal, stream>>>(tm_a, tm_w, tm_a2, tm_w2, tm_out, tm_res,
+                                                                       tm_out2, p);
   return check_cuda(cudaGetLastError(), "gemm2_kernel launch");
 }
 
@@ -996,6 +1089,7 @@ int launch(const dod_gemm_args& a, cudaStream_t stream, bool direct) {
   p.direct = direct;
   p.a_trans = a.a_trans;
   p.w_trans = a.w_trans;
+  fill_ln_params(p, a);
   const int tiles = p.tiles_m * p.tiles_n * p.batch;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   gemm_kernel<BN, RES, TRANS><<<grid, kThreads, L::kTotal, stream>>>(tm_a, tm_w, tm_a2, tm_w2, tm_out, tm_res, p);
@@ -1066,6 +1160,23 @@ extern "C" int32_t dod_gemm_bf16(const dod_gemm_args* a, dod_stream_t stream_) {
                 "dod_gemm_bf16: a2/w2 must be 16-byte aligned");
   }
   DOD_REQUIRE(a->act >= DOD_ACT_NONE && a->act <= DOD_ACT_SWIGLU, "dod_gemm_bf16: bad act");
+  if (a->out_bf16 || a->row_stats_out) {
+    // folded LayerNorm, producer side: only the CTA-pair kernel's residual epilogue implements it
+    DOD_REQUIRE(a->out_bf16 && a->row_stats_out, "dod_gemm_bf16: out_bf16 and row_stats_out come together");
+    DOD_REQUIRE(a->residual && a->out_dtype == DOD_F32 && a->m >= 512 && a->n >= 256 && a->n % 16 == 0 &&
+                    a->patch_rows == 0 && a->batch <= 1 && a->batch_inner <= 1 && use_pair_kernel(),
+                "dod_gemm_bf16: out_bf16 / row_stats_out need a residual GEMM with fp32 output, m >= 512, "
+                "n >= 256, n %% 16 == 0");
+    DOD_REQUIRE(a->ldo_bf16 >= a->n && a->ldo_bf16 % 8 == 0 && (uintptr_t(a->out_bf16) & 15) == 0 &&
+                    (uintptr_t(a->row_stats_out) & 7) == 0,
+                "dod_gemm_bf16: out_bf16 needs ldo_bf16 >= n, ldo_bf16 %% 8 == 0 and 16-byte alignment");
+  }
+  if (a->row_scale) {
+    DOD_REQUIRE(a->bias, "dod_gemm_bf16: row_scale needs a bias (folded LayerNorm: b + W beta)");
+    DOD_REQUIRE(a->patch_rows == 0 && !(a->residual && a->out_dtype != DOD_F32) && a->batch <= 1 &&
+                    a->batch_inner <= 1 && a->n % 8 == 0 && (uintptr_t(a->row_scale) & 3) == 0,
+                "dod_gemm_bf16: row_scale is not available with patch rows / bf16 residual output / batches");
+  }
   if (a->batch_inner > 1) {
     DOD_REQUIRE(a->inner_stride_a % 8 == 0 && a->inner_stride_w % 8 == 0 &&
                     a->inner_stride_out % (a->out_dtype == DOD_F32 ? 4 : 8) == 0 && a->inner_stride_a > 0 &&

@@ -48,9 +48,21 @@ class PackedLinear:
     lora   None or (PackedLinear for x -> t, packed alpha*B as second K segment, k2)
     """
 
-    def __init__(self, weight, bias, mode, *, lora=None, swiglu_interleave=False):
+    def __init__(self, weight, bias, mode, *, lora=None, swiglu_interleave=False, ln=None):
         # weight: f32 [N, K] (detached, on device); lora: (A [r_tot, K], B_full [N, r_tot]) f32
+        # ln = (gamma, beta, eps): fold the LayerNorm in front of this projection into it (bf16 mode, no
+        # LoRA): W'' = gamma (.) W minus its row means (zero-sum rows remove the mean of h inside the
+        # product), bias' = bias + W beta; the GEMM is then fed the un-normalised bf16 residual stream and
+        # scales its accumulator by the row's rstd (include/dod.h)
         n, k = weight.shape
+        self.ln = None
+        if ln is not None:
+            assert mode == "bf16" and lora is None
+            gamma, beta, eps = ln
+            fold_b = weight @ beta
+            bias = fold_b if bias is None else bias + fold_b
+            weight = weight * gamma[None, :]
+            weight = weight - weight.mean(dim=1, keepdim=True)
         self.mode, self.n, self.k = mode, n, k
         self.n_pad = _pad8(n)
         perm = None
@@ -66,6 +78,8 @@ class PackedLinear:
         if bias is not None:
             self.bias = torch.zeros(self.n_pad, dtype=torch.float32, device=weight.device)
             self.bias[:n].copy_(bias)
+        if ln is not None:
+            self.ln = (k, float(ln[2]))
         self.lora = None
         if lora is not None:
             a_mat, b_mat = lora                                # [r, K], [N, r] (alpha folded into B)
@@ -98,16 +112,20 @@ class PackedLinear:
         return ops.split3_bf16(x, _pad8(x.shape[1]), w_side=False)
 
     def __call__(self, x, *, act=ACT_NONE, scale=None, residual=None, out=None, out_dtype=None,
-                 patch_rows=0, out_rows=None):
+                 patch_rows=0, out_rows=None, ln_out=None, row_stats=None, rstd_buf=None):
         adt = torch.bfloat16 if self.mode == "bf16" else torch.float32
         a = self._operand(x)
+        row_scale = None
+        if self.ln is not None:
+            assert row_stats is not None, "this pack has a LayerNorm folded in: pass the producer's row_stats"
+            row_scale = ops.ln_rstd(row_stats, *self.ln, out=rstd_buf)
         a2 = w2 = None
         if self.lora is not None:
             t = self.lora[0](x, out_dtype=adt)                 # x.A^T  [M, r_pad]
             a2, w2 = self.lora[0]._operand(t), self.lora[1]
         return ops.gemm(a, self.w, self.bias, act=act, scale=scale, residual=residual, out=out,
                         out_dtype=out_dtype or adt, a2=a2, w2=w2, patch_rows=patch_rows,
-                        out_rows=out_rows)
+                        out_rows=out_rows, ln_out=ln_out, row_scale=row_scale)
 
 
 def _lin_parts(mod):
@@ -122,7 +140,7 @@ def _lin_parts(mod):
     return w, b, None, None
 
 
-def pack_linears(mods, mode, *, swiglu_interleave=False):
+def pack_linears(mods, mode, *, swiglu_interleave=False, ln=None):
     """Concatenate one or more (Lora)Linear containers along N into one PackedLinear.
     LoRA pairs become one [sum r, K] A matrix and a block-diagonal B."""
     parts = [_lin_parts(m) for m in mods]
@@ -143,7 +161,7 @@ def pack_linears(mods, mode, *, swiglu_interleave=False):
                 r0 += r
             n0 += n
         lora = (a_cat, b_full)
-    return PackedLinear(w, b, mode, lora=lora, swiglu_interleave=swiglu_interleave)
+    return PackedLinear(w, b, mode, lora=lora, swiglu_interleave=swiglu_interleave, ln=ln)
 
 
 def pack_raw(weight, bias, mode):
@@ -168,6 +186,11 @@ def params_version(module):
 
 def f32c(t):
     return t.detach().float().contiguous()
+
+
+def ln_fold_enabled():
+    """DOD_LN_FOLD=0 keeps every LayerNorm a standalone kernel (A/B measurements)."""
+    return os.environ.get("DOD_LN_FOLD", "1") != "0"
 
 
 # ---------------------------------------------------------------------------
@@ -204,6 +227,14 @@ class BackbonePack:
             else:
                 L["fc1"] = pack_linears([lyr.mlp.fc1], mode)
                 L["fc2"] = pack_linears([lyr.mlp.fc2], mode)
+            # LayerNorm folded into the following projection (bf16 mode, LoRA-free blocks): see
+            # backbone_forward.  Both forms are kept: small batches (< 512 token rows) use the plain one.
+            if mode == "bf16" and ln_fold_enabled() and L["qkv"].lora is None:
+                L["qkv_ln"] = pack_linears([att.attention.query, att.attention.key, att.attention.value], mode,
+                                           ln=L["n1"] + (1e-6,))
+                first = lyr.mlp.weights_in if self.swiglu else lyr.mlp.fc1
+                if L["w_in" if self.swiglu else "fc1"].lora is None:
+                    L["mlp_ln"] = pack_linears([first], mode, swiglu_interleave=self.swiglu, ln=L["n2"] + (1e-6,))
             self.layers.append(L)
         self.final_ln = (f32c(dino.layernorm.weight), f32c(dino.layernorm.bias))
         self.proj = pack_linears([bk.projection], mode) if bk.projection is not None else None
@@ -255,21 +286,40 @@ def backbone_forward(pack: BackbonePack, pixel_values, final_norm=True):
     else:
         ops.gemm(patches, pack.patch.w, pack.patch.bias, residual=pos, out=x, patch_rows=p)
     scale = 1.0 / math.sqrt(64.0)
-    for L in pack.layers:
-        hN = ops.layernorm(x, *L["n1"], 1e-6, out_dtype=adt)
-        qkv = L["qkv"](hN)                                                  # [M, 3D]
+    # Folded LayerNorm (bf16 mode, >= 512 token rows, LoRA-free blocks): the residual GEMM in front of a
+    # LayerNorm also writes the bf16 copy of the new residual stream and per-row partial sums, and the
+    # projection behind it runs on that copy with gamma folded into zero-sum weight rows and the row's rstd
+    # applied in its epilogue (include/dod.h) -- the 404 MB/layer-norm HBM pass disappears.
+    fold = mode == "bf16" and m >= 512 and d % 16 == 0
+    h16 = stats = rstd = None
+    if fold and any("qkv_ln" in L or "mlp_ln" in L for L in pack.layers):
+        h16 = torch.empty((m, d), dtype=torch.bfloat16, device=px.device)
+        stats = torch.empty((2 * ((d + 255) // 256), m, 2), dtype=torch.float32, device=px.device)
+        rstd = torch.empty(m, dtype=torch.float32, device=px.device)
+    have_n1 = False     # h16 / stats hold the current residual stream (written by the previous fc2)
+    for i, L in enumerate(pack.layers):
+        if have_n1:
+            qkv = L["qkv_ln"](h16, row_stats=stats, rstd_buf=rstd)
+        else:
+            hN = ops.layernorm(x, *L["n1"], 1e-6, out_dtype=adt)
+            qkv = L["qkv"](hN)                                              # [M, 3D]
         if mode == "bf16":
             ctx = ops.fmha(qkv, b, n, pack.heads, q_off=0, k_off=d, v_off=2 * d, scale=scale)
         else:
             ctx = ops.mha_small(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], b, n, n, pack.heads, 64, scale)
-        L["proj"](ctx, scale=L["ls1"], residual=x, out=x)                   # x += ls1 * (ctx Wo^T + b)
-        hN = ops.layernorm(x, *L["n2"], 1e-6, out_dtype=adt)
-        if pack.swiglu:
-            a = L["w_in"](hN, act=ACT_SWIGLU)
-            L["w_out"](a, scale=L["ls2"], residual=x, out=x)
+        fold_n2 = fold and "mlp_ln" in L
+        nxt = pack.layers[i + 1] if i + 1 < len(pack.layers) else None
+        have_n1 = fold and nxt is not None and "qkv_ln" in nxt
+        # x += ls1 * (ctx Wo^T + b)
+        L["proj"](ctx, scale=L["ls1"], residual=x, out=x, ln_out=(h16, stats) if fold_n2 else None)
+        first, second = ("w_in", "w_out") if pack.swiglu else ("fc1", "fc2")
+        act = ACT_SWIGLU if pack.swiglu else ACT_GELU_ERF
+        if fold_n2:
+            a = L["mlp_ln"](h16, act=act, row_stats=stats, rstd_buf=rstd)
         else:
-            a = L["fc1"](hN, act=ACT_GELU_ERF)
-            L["fc2"](a, scale=L["ls2"], residual=x, out=x)
+            hN = ops.layernorm(x, *L["n2"], 1e-6, out_dtype=adt)
+            a = L[first](hN, act=act)
+        L[second](a, scale=L["ls2"], residual=x, out=x, ln_out=(h16, stats) if have_n1 else None)
     if not final_norm:
         return x, b, n
     mem = ops.layernorm(x, *pack.final_ln, 1e-6, out_dtype=adt)

@@ -66,10 +66,15 @@ def _rowmajor(t: torch.Tensor, name: str):
 
 
 def gemm(a, w, bias=None, *, act=ACT_NONE, scale=None, residual=None, out=None,
-         out_dtype=torch.bfloat16, a2=None, w2=None, patch_rows=0, out_rows=None, a_trans=False, w_trans=False):
+         out_dtype=torch.bfloat16, a2=None, w2=None, patch_rows=0, out_rows=None, a_trans=False, w_trans=False,
+         ln_out=None, row_scale=None):
     """out = residual + scale * act(a @ w.T (+ a2 @ w2.T) + bias); a, w (a2, w2) bf16.
     a_trans: `a` is the stored transpose [K, M] (out = a.T @ ...); w_trans: `w` is stored [K, N]
-    (out = ... @ w) -- the kernel reads them as MN-major operands, no transposed copy is made."""
+    (out = ... @ w) -- the kernel reads them as MN-major operands, no transposed copy is made.
+    Folded LayerNorm (include/dod.h): ln_out=(h_bf16 [M, N], row_stats [2*ceil(N/256), M, 2]) makes a residual
+    GEMM also emit the bf16 copy of its output and per-row partial sums; row_scale (f32 [M], = ln_rstd(row_stats))
+    makes the epilogue multiply the accumulator of row m by row_scale[m] before bias / activation (the weights
+    then carry gamma and have zero-sum rows, the bias carries W beta)."""
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
     lda, ldw = _rowmajor(a, "a"), _rowmajor(w, "w")
     k, m = (a.shape if a_trans else a.shape[::-1])
@@ -88,6 +93,15 @@ def gemm(a, w, bias=None, *, act=ACT_NONE, scale=None, residual=None, out=None,
         assert a2.dtype == torch.bfloat16 and w2.dtype == torch.bfloat16
         assert a2.shape[0] == m and w2.shape[0] == n and a2.shape[1] == w2.shape[1]
         kw.update(a2=a2, w2=w2, k2=a2.shape[1], lda2=_rowmajor(a2, "a2"), ldw2=_rowmajor(w2, "w2"))
+    if ln_out is not None:
+        h16, stats = ln_out
+        assert h16.dtype == torch.bfloat16 and stats.dtype == torch.float32 and h16.shape[0] >= m
+        assert stats.is_contiguous() and tuple(stats.shape) == (2 * ((n + 255) // 256), m, 2)
+        kw.update(out_bf16=h16, ldo_bf16=_rowmajor(h16, "ln_out"), row_stats_out=stats)
+    if row_scale is not None:
+        assert row_scale.dtype == torch.float32 and row_scale.is_contiguous() and row_scale.numel() >= m
+        assert bias is not None
+        kw.update(row_scale=row_scale)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() >= n
     if scale is not None:
@@ -97,6 +111,17 @@ def gemm(a, w, bias=None, *, act=ACT_NONE, scale=None, residual=None, out=None,
     k_tot = k + (a2.shape[1] if a2 is not None else 0)
     with _Timed("gemm", 2.0 * m * n * k_tot):
         _dod.call("dod_gemm_bf16", _stream(a), **kw)
+    return out
+
+
+def ln_rstd(row_stats, dim, eps, out=None):
+    """rstd [M] from the partial sums [slots, M, 2] a residual GEMM wrote through ln_out (folded LayerNorm)."""
+    slots, m, _ = row_stats.shape
+    assert row_stats.dtype == torch.float32 and row_stats.is_contiguous()
+    if out is None:
+        out = torch.empty(m, dtype=torch.float32, device=row_stats.device)
+    _dod.call("dod_ln_rstd", _stream(row_stats), row_stats=row_stats, rstd=out, slots=slots, rows=m, dim=int(dim),
+              eps=float(eps))
     return out
 
 

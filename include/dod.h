@@ -98,8 +98,34 @@ typedef struct {
    * stride ldw >= N.  The tiles are then fed to tcgen05.mma as MN-major operands.  Not combined with
    * the second K segment (a2 / w2).                                                                 */
   int32_t a_trans, w_trans;
+  /* LayerNorm folded across two GEMMs (the frozen, LoRA-free encoder blocks in bf16 mode; replaces the
+   * standalone nn.LayerNorm pass of modeling_dinov2.py:354,359 between a residual GEMM and the next
+   * projection).  With W'' = gamma (.) W minus its row means (every row of W'' sums to zero, so the
+   * product removes the row mean of h by itself):
+   *     LN(h) . W^T + b  =  rstd_m * ( h . W''^T )  +  ( b + W . beta )_n
+   * PRODUCER side (a residual GEMM with fp32 output, m >= 512, n >= 256, n % 16 == 0): besides `out`
+   * (the fp32 residual stream h) it writes h rounded to bf16 to `out_bf16` (row stride ldo_bf16) and
+   * per-row partial sums of h and h^2 to `row_stats_out` [2 * ceil(n / 256)][M][2] f32 (one slot per
+   * 128 columns, slot-major so that a warp's 32 rows are contiguous; written without atomics so the result is run-to-run reproducible).
+   * dod_ln_rstd then reduces the slots to rstd[M] (a 4 MB pass), and on the CONSUMER side (bf16 h as `a`,
+   * W'' as `w`, the folded bias as `bias`) `row_scale` = rstd: the epilogue multiplies the accumulator of
+   * row m by row_scale[m] before bias / activation.                                                   */
+  void* out_bf16;
+  int64_t ldo_bf16;
+  float* row_stats_out;
+  const float* row_scale; /* f32 [M] or NULL */
 } dod_gemm_args;
 DOD_API int32_t dod_gemm_bf16(const dod_gemm_args* a, dod_stream_t stream);
+
+/* rstd[m] = rsqrt(var_m + eps) from the per-row partial sums a producer GEMM wrote (folded LayerNorm above;
+ * nn.LayerNorm statistics of modeling_dinov2.py:354,359 in fp32).                                        */
+typedef struct {
+  const float* row_stats; /* f32 [slots][rows][2]: partial sums of h and h^2 */
+  float* rstd;            /* f32 [rows]                                      */
+  int64_t slots, rows, dim;
+  float eps;
+} dod_ln_rstd_args;
+DOD_API int32_t dod_ln_rstd(const dod_ln_rstd_args* a, dod_stream_t stream);
 
 /* ---- LayerNorm (HBM-bound) ----------------------------------------------
  * y = (x - mean) * rsqrt(var + eps) * gamma + beta, fp32 statistics.

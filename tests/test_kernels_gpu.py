@@ -151,6 +151,59 @@ def test_gemm_fp32_mode_split3(ops):
 
 
 # ----------------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("m,d,n2,act", [(514, 384, 1152, "none"), (2740, 768, 3072, "gelu"), (1000, 1024, 3072, "none"),
+                                       (700, 1536, 4096, "swiglu")])
+def test_gemm_folded_layernorm(ops, m, d, n2, act):
+    """LayerNorm folded across two GEMMs (include/dod.h): a residual GEMM that also emits bf16(h) and
+    per-row partial sums, then a projection of h with gamma folded into zero-sum weight rows and the rstd
+    scaling in its epilogue -- against  act(LayerNorm(h) @ W^T + b)  in fp32 torch."""
+    g = _gen(m + d + n2)
+    k1 = 256
+    a = _randn((m, k1), g).bfloat16()
+    w1 = _randn((d, k1), g, 1 / math.sqrt(k1)).bfloat16()
+    b1 = _randn((d,), g)
+    ls = _randn((d,), g)
+    x = _randn((m, d), g) + 0.3                      # residual stream with a non-zero row mean
+    h_ref = x + ls * (a.float() @ w1.float().t() + b1)
+    h16 = torch.empty((m, d), dtype=torch.bfloat16, device="cuda")
+    slots = 2 * ((d + 255) // 256)
+    stats = torch.full((slots, m, 2), float("nan"), device="cuda")
+    h = ops.gemm(a, w1, b1, scale=ls, residual=x, out_dtype=torch.float32, ln_out=(h16, stats))
+    assert _rel(h, h_ref) < 2e-5
+    assert torch.equal(h16, h.bfloat16())
+    assert torch.allclose(stats[:, :, 0].sum(0), h.sum(1), rtol=1e-4, atol=1e-3)
+    assert torch.allclose(stats[:, :, 1].sum(0), (h * h).sum(1), rtol=1e-4, atol=1e-3)
+
+    gamma = 1.0 + 0.2 * _randn((d,), g)
+    beta = 0.1 * _randn((d,), g)
+    w2 = _randn((n2, d), g, 1 / math.sqrt(d))
+    b2 = _randn((n2,), g)
+    eps = 1e-6
+    ln = torch.nn.functional.layer_norm(h, (d,), gamma, beta, eps)
+    ref = ln @ w2.t() + b2
+    w2f = w2 * gamma[None, :]
+    w2f = (w2f - w2f.mean(dim=1, keepdim=True)).bfloat16()      # zero-sum rows: the product drops the row mean
+    b2f = b2 + w2 @ beta
+    dod_act = ops.ACT_NONE
+    if act == "gelu":
+        ref = torch.nn.functional.gelu(ref)
+        dod_act = ops.ACT_GELU_ERF
+    elif act == "swiglu":
+        half = n2 // 2
+        ref = torch.nn.functional.silu(ref[:, :half]) * ref[:, half:]
+        idx = torch.arange(n2, device="cuda").view(2, half // 128, 128).permute(1, 0, 2).reshape(-1)
+        w2f, b2f = w2f[idx].contiguous(), b2f[idx].contiguous()
+        dod_act = ops.ACT_SWIGLU
+    out = ops.gemm(h16, w2f, b2f, act=dod_act, row_scale=ops.ln_rstd(stats, d, eps))
+    # same bf16-operand tolerance as the unfolded path (bf16 activations / weights / output)
+    assert _rel(out, ref) < 2e-2
+    unfolded = ops.gemm(ln.bfloat16(), w2.bfloat16() if act != "swiglu" else w2.bfloat16()[idx].contiguous(),
+                        b2 if act != "swiglu" else b2[idx].contiguous(), act=dod_act)
+    err_f = (out.float() - ref).abs().mean().item()
+    err_u = (unfolded.float() - ref).abs().mean().item()
+    assert err_f < 2.0 * err_u + 1e-4, (err_f, err_u)
+
+
 @pytest.mark.parametrize("d", [256, 384, 768, 1024, 1536])
 @pytest.mark.parametrize("xdt", [torch.float32, torch.bfloat16])
 def test_layernorm(ops, d, xdt):

@@ -23,6 +23,44 @@ for name, (n, k, res, act) in shapes.items():
     ms = e0.elapsed_time(e1) / 20
     print(f"{name:5s} N={n:4d} K={k:4d}: {ms*1e3:7.1f} us  {2*m*n*k/ms/1e9:6.0f} TFLOP/s")
 
+# LayerNorm folded across two GEMMs: producer (residual GEMM + bf16 copy + row partial sums) and consumer
+# (rstd scaling in the epilogue) variants of the same shapes, timed ALTERNATELY with the plain form (the
+# chip's clock under the power cap drifts over a run, so back-to-back blocks are not comparable)
+d = 768
+h16 = torch.empty((m, d), dtype=torch.bfloat16, device="cuda")
+stats = torch.zeros((2 * ((d + 255) // 256), m, 2), device="cuda")
+stats[:, :, 1] = 128.0   # var = 1, rstd = 1
+rstd = ops.ln_rstd(stats, d, 1e-6)
+
+
+def timeit(f, n=20):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): f()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3
+
+
+for name, (n, k, res, act) in shapes.items():
+    a, w = rnd(m, k), rnd(n, k)
+    bias = torch.randn(n, device="cuda") * 0.1
+    scale = torch.ones(n, device="cuda") if res else None
+    r = torch.randn(m, n, device="cuda") if res else None
+    out = torch.empty((m, n), dtype=torch.float32 if res else torch.bfloat16, device="cuda")
+    plain = lambda: ops.gemm(a, w, bias, act=act, scale=scale, residual=r, out=out)
+    if res:
+        fold = lambda: ops.gemm(a, w, bias, act=act, scale=scale, residual=r, out=out, ln_out=(h16, stats))
+    else:
+        fold = lambda: ops.gemm(a, w, bias, act=act, out=out, row_scale=rstd)
+    for _ in range(3): plain(); fold()
+    tp, tf = [], []
+    for _ in range(5):
+        tp.append(timeit(plain)); tf.append(timeit(fold))
+    tp.sort(); tf.sort()
+    print(f"{name:5s} plain {tp[2]:7.1f} us (min {tp[0]:.1f})   folded-LN {'producer' if res else 'consumer'} {tf[2]:7.1f} us (min {tf[0]:.1f})")
+if "--no-cublas" in sys.argv: sys.exit(0)
+
 # library bar on the same shapes: torch.matmul (cuBLASLt), bf16 in / bf16 out, no epilogue at all
 for name, (n, k, res, act) in shapes.items():
     a, w = rnd(m, k), rnd(n, k)
