@@ -200,7 +200,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
 
 
 def run_ours(args):
@@ -343,9 +343,12 @@ def run_ours(args):
                                                              "stream, outputs copied back every step"},
         "gpu_launches": int(launches), "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+_RESULT_OUT = sys.stdout
 
 
 def main():
@@ -357,6 +360,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # stdout carries exactly ONE line (the JSON result): libraries that write to fd 1 on their own (NCCL prints
+    # its version banner there when NCCL_DEBUG=VERSION/INFO) are sent to stderr for the duration of the run
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -128,11 +128,23 @@ class PackedLinear:
                         out_rows=out_rows, ln_out=ln_out, row_scale=row_scale)
 
 
-def _lin_parts(mod):
-    """(weight, bias, loraA, alpha*loraB) of an nn.Linear or LoraLinear container (detached f32)."""
+def lora_merge_enabled():
+    """Inference packs (bf16 mode) carry W + alpha.B.A as ONE matrix: the skinny x.A^T GEMM (a second pass over
+    the activations) and the extra K segment disappear, and the block becomes eligible for LayerNorm folding.
+    The two-segment form (dod_gemm_bf16's a2 / w2) stays the training path, where A and B change every step.
+    DOD_LORA_MERGE=0 keeps the two-segment form for inference too (A/B measurements, parity tests of it)."""
+    return os.environ.get("DOD_LORA_MERGE", "1") != "0"
+
+
+def _lin_parts(mod, merge=False):
+    """(weight, bias, loraA, alpha*loraB) of an nn.Linear or LoraLinear container (detached f32).
+    merge: return (W + alpha.B.A, bias, None, None) for a LoraLinear (reference utils.py:68-70 evaluated in fp32)."""
     from .utils import LoraLinear
     if isinstance(mod, LoraLinear):
         w, b = mod.linear.weight.detach(), (mod.linear.bias.detach() if mod.linear.bias is not None else None)
+        if merge:
+            w_eff = w.float() + float(mod.alpha) * (mod.lora_B.weight.detach().float() @ mod.lora_A.weight.detach().float())
+            return w_eff, (b.float() if b is not None else None), None, None
         return w.float(), (b.float() if b is not None else None), mod.lora_A.weight.detach().float(), \
             mod.lora_B.weight.detach().float() * float(mod.alpha)
     w = mod.weight.detach().float()
@@ -140,10 +152,10 @@ def _lin_parts(mod):
     return w, b, None, None
 
 
-def pack_linears(mods, mode, *, swiglu_interleave=False, ln=None):
+def pack_linears(mods, mode, *, swiglu_interleave=False, ln=None, merge_lora=False):
     """Concatenate one or more (Lora)Linear containers along N into one PackedLinear.
-    LoRA pairs become one [sum r, K] A matrix and a block-diagonal B."""
-    parts = [_lin_parts(m) for m in mods]
+    LoRA pairs become one [sum r, K] A matrix and a block-diagonal B (or are merged into W: merge_lora)."""
+    parts = [_lin_parts(m, merge_lora) for m in mods]
     w = torch.cat([p[0] for p in parts], dim=0)
     b = None
     if any(p[1] is not None for p in parts):
@@ -197,7 +209,9 @@ def ln_fold_enabled():
 # backbone (HF Dinov2Model restated as a kernel sequence)
 # ---------------------------------------------------------------------------
 class BackbonePack:
-    def __init__(self, bk, mode):
+    def __init__(self, bk, mode, n_layers=None):
+        """n_layers: pack only the embeddings and the first n_layers blocks (the frozen part the training
+        forward runs with the inference kernels); None packs everything for inference."""
         dino = bk.dino
         emb = dino.embeddings
         self.mode = mode
@@ -211,33 +225,38 @@ class BackbonePack:
         self.pos = f32c(emb.position_embeddings.reshape(-1, d))
         self.pos_cache = {}
         self.layers = []
-        for lyr in dino.encoder.layer:
+        merge = mode == "bf16" and lora_merge_enabled()
+        blocks = list(dino.encoder.layer)
+        for lyr in (blocks if n_layers is None else blocks[:n_layers]):
             att = lyr.attention
+            qkv_mods = [att.attention.query, att.attention.key, att.attention.value]
             L = dict(
                 n1=(f32c(lyr.norm1.weight), f32c(lyr.norm1.bias)),
-                qkv=pack_linears([att.attention.query, att.attention.key, att.attention.value], mode),
-                proj=pack_linears([att.output.dense], mode),
+                qkv=pack_linears(qkv_mods, mode, merge_lora=merge),
+                proj=pack_linears([att.output.dense], mode, merge_lora=merge),
                 ls1=f32c(lyr.layer_scale1.lambda1),
                 n2=(f32c(lyr.norm2.weight), f32c(lyr.norm2.bias)),
                 ls2=f32c(lyr.layer_scale2.lambda1),
             )
             if self.swiglu:
-                L["w_in"] = pack_linears([lyr.mlp.weights_in], mode, swiglu_interleave=True)
-                L["w_out"] = pack_linears([lyr.mlp.weights_out], mode)
+                L["w_in"] = pack_linears([lyr.mlp.weights_in], mode, swiglu_interleave=True, merge_lora=merge)
+                L["w_out"] = pack_linears([lyr.mlp.weights_out], mode, merge_lora=merge)
             else:
-                L["fc1"] = pack_linears([lyr.mlp.fc1], mode)
-                L["fc2"] = pack_linears([lyr.mlp.fc2], mode)
-            # LayerNorm folded into the following projection (bf16 mode, LoRA-free blocks): see
+                L["fc1"] = pack_linears([lyr.mlp.fc1], mode, merge_lora=merge)
+                L["fc2"] = pack_linears([lyr.mlp.fc2], mode, merge_lora=merge)
+            # LayerNorm folded into the following projection (bf16 mode, no separate LoRA segment): see
             # backbone_forward.  Both forms are kept: small batches (< 512 token rows) use the plain one.
             if mode == "bf16" and ln_fold_enabled() and L["qkv"].lora is None:
-                L["qkv_ln"] = pack_linears([att.attention.query, att.attention.key, att.attention.value], mode,
-                                           ln=L["n1"] + (1e-6,))
+                L["qkv_ln"] = pack_linears(qkv_mods, mode, ln=L["n1"] + (1e-6,), merge_lora=merge)
                 first = lyr.mlp.weights_in if self.swiglu else lyr.mlp.fc1
                 if L["w_in" if self.swiglu else "fc1"].lora is None:
-                    L["mlp_ln"] = pack_linears([first], mode, swiglu_interleave=self.swiglu, ln=L["n2"] + (1e-6,))
+                    L["mlp_ln"] = pack_linears([first], mode, swiglu_interleave=self.swiglu, ln=L["n2"] + (1e-6,),
+                                               merge_lora=merge)
             self.layers.append(L)
-        self.final_ln = (f32c(dino.layernorm.weight), f32c(dino.layernorm.bias))
-        self.proj = pack_linears([bk.projection], mode) if bk.projection is not None else None
+        self.final_ln = self.proj = None
+        if n_layers is None:
+            self.final_ln = (f32c(dino.layernorm.weight), f32c(dino.layernorm.bias))
+            self.proj = pack_linears([bk.projection], mode) if bk.projection is not None else None
 
     def pos_for(self, h, w):
         """HF interpolate_pos_encoding (modeling_dinov2.py:57-95): identity at the native square

@@ -379,17 +379,12 @@ def train_forward(model, pixel_values):
     if _engine.resolve_precision(model.precision) != "bf16":
         raise NotImplementedError("the libdod training path runs in bf16 mode (fp32 mode is inference-only)")
     st = TrainState()
-    pack = bk._get_pack()                       # frozen blocks reuse the inference pack
     dino = bk.dino
     n_layers = len(dino.encoder.layer)
     n_train = min(2, n_layers)
     heads = dino.num_heads
-    # ---- embeddings + frozen blocks (inference kernels, nothing saved) ----
-    frozen_only = _engine.BackbonePack.__new__(_engine.BackbonePack)
-    frozen_only.__dict__.update(pack.__dict__)
-    frozen_only.layers = pack.layers[:n_layers - n_train]
-    frozen_only.proj = None
-    x, b, n = _engine.backbone_forward(frozen_only, pixel_values, final_norm=False)
+    # ---- embeddings + frozen blocks (inference kernels, nothing saved; packed once, not per step) ----
+    x, b, n = _engine.backbone_forward(bk._get_frozen_pack(n_layers - n_train), pixel_values, final_norm=False)
     st.b, st.n, st.heads = b, n, heads
     # ---- LoRA blocks ----
     cache = bk.__dict__.setdefault("_train_frozen_cache", {})

@@ -155,6 +155,18 @@ class DINOv2Backbone(nn.Module):
             self._pack_key = key
         return self._pack
 
+    def _get_frozen_pack(self, n_layers):
+        """Embeddings + the first n_layers (frozen) blocks for the training forward.  Keyed on THOSE parameters
+        only: the LoRA / projection updates of every optimizer step do not trigger a re-pack of 100+ MB of
+        frozen weights (the whole-backbone key of _get_pack did, 140 cast launches per training step)."""
+        mode = _engine.resolve_precision(self.precision)
+        mods = [self.dino.embeddings] + list(self.dino.encoder.layer)[:n_layers]
+        key = (mode, n_layers) + tuple((p.data_ptr(), p._version) for m in mods for p in m.parameters())
+        if getattr(self, "_fpack", None) is None or self._fpack_key != key:
+            self._fpack = _engine.BackbonePack(self, mode, n_layers=n_layers)
+            self._fpack_key = key
+        return self._fpack
+
     def forward_rows(self, pixel_values):
         """-> (memory [B*N, out_dim] in the activation dtype, B, N)."""
         return _engine.backbone_forward(self._get_pack(), pixel_values)

@@ -48,6 +48,20 @@ def test_bf16_mode_matches_reference_golden(case):
     assert (b > 0).all() and (b < 1).all()
 
 
+@pytest.mark.parametrize("case", ["c1_small_deform", "base_518", "giant3_swiglu"])
+@pytest.mark.parametrize("env", [{"DOD_LORA_MERGE": "0"}, {"DOD_LN_FOLD": "0"},
+                                 {"DOD_LORA_MERGE": "0", "DOD_LN_FOLD": "0"}])
+def test_bf16_mode_unmerged_unfolded_forms(case, env, monkeypatch):
+    """The default bf16 inference pack merges LoRA into W and folds LayerNorm into the neighbouring GEMMs;
+    the two-segment LoRA GEMM and the standalone LayerNorm pass stay selectable and meet the same bar."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    out, sd, kw, x = _run(case, "bf16")
+    g = golden("detector_" + case)
+    assert rel_err(out["pred_logits"], torch.from_numpy(g["pred_logits"])) < 2e-2
+    assert rel_err(out["pred_boxes"], torch.from_numpy(g["pred_boxes"])) < 2e-2
+
+
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
 def test_backbone_memory_matches_oracle(precision, tol):
     """backbone.forward (reference dinov2_backbone.py:58-67) incl. LoRA on the last two blocks."""
