@@ -43,6 +43,11 @@ constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr int kChunkBytes = 32 * 64;  // one epilogue chunk buffer: 32 rows x 64 B
+#ifdef DOD_GEMM_NARROW
+constexpr bool kWideStores = false;  // A/B builds (tools/build_variant.sh narrow gemm.cu -DDOD_GEMM_NARROW)
+#else
+constexpr bool kWideStores = true;   // CTA-pair kernel, no residual: 128-byte-row TMA stores
+#endif
 
 struct GemmParams {
   int M, N, K1blocks, K2blocks;
@@ -150,7 +155,11 @@ __device__ __forceinline__ uint32_t sw64(int r, int j) { return r * 64 + ((j ^ (
 
 // Epilogue of one tile through shared memory, in chunks of COLS output columns
 // (16 fp32 or 32 bf16 = 64 bytes per row).
-template <int BN, bool RES, bool OUT_F32>
+// WIDE: the warp handles PAIRS of adjacent chunks and stores them with one TMA box of 128-byte rows (4 KB,
+// 128B-swizzled) instead of two boxes of 64-byte rows.  The TMA unit's cost is per ROW, not per byte (~2.7
+// clk per row for 64 B and 128 B rows alike -- the figure that also paces the mainloop's operand loads), so
+// halving the epilogue's row count shortens every tile (profiles/r01_summary.md).
+template <int BN, bool RES, bool OUT_F32, bool WIDE = false>
 __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUtensorMap* tm_out,
                                                   const CUtensorMap* tm_res, uint32_t t_row, int bz,
                                                   int mb, int nb, int quad, int half, int lane,
@@ -159,7 +168,10 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
                                                   uint32_t& res_issue, uint32_t& res_wait,
                                                   uint32_t tempty_addr, uint64_t* tfull_bar,
                                                   uint32_t tfull_phase, float ln_rstd = 0.0f) {
+  static_assert(!(RES && WIDE), "the wide store path has no residual prefetch");
   constexpr int COLS = OUT_F32 ? 16 : 32;
+  constexpr int STEP = WIDE ? 4 : 2;  // chunks between the starts of this warp's consecutive groups
+  constexpr int SUBS = WIDE ? 2 : 1;  // chunks per group (= per TMA store)
   const bool swiglu = p.act == DOD_ACT_SWIGLU;
   const int width = swiglu ? BN / 2 : BN;  // output columns of this tile
   const int nch = width / COLS;
@@ -181,8 +193,13 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
   mbar_wait(tfull_bar, tfull_phase);
   tc_fence_after();
 
+  bool group_ok = false;  // WIDE: the group's first chunk is inside N and M (a store will be issued)
+  uint8_t* ob = out_buf;
 #pragma unroll 1
-  for (int c = half; c < nch; c += 2) {
+  for (int c0 = half * SUBS; c0 < nch; c0 += STEP)
+#pragma unroll 1
+  for (int sub = 0; sub < SUBS; ++sub) {
+    const int c = c0 + sub;
     const int n0 = col_base + c * COLS;  // first output column of the chunk
     if constexpr (RES) {
       if (c + 2 < nch) {
@@ -199,7 +216,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
     tmem_ld_cols<COLS>(t_row + c * COLS, v);
     if (swiglu) tmem_ld_cols<COLS>(t_row + BN / 2 + c * COLS, u);
     tmem_ld_wait();
-    if (c + 2 >= nch) {
+    if (c0 + STEP >= nch && sub == SUBS - 1) {
       // this warp has read its share of the accumulator: hand the TMEM stage back
       tc_fence_before();
       __syncwarp();
@@ -287,33 +304,77 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, const CUt
     // Rotating them without committing a store let a later chunk overwrite a buffer whose TMA store
     // was still in flight (wait_group.read<1> only covers COMMITTED groups): the last valid chunk of a
     // mostly-empty N tile was then written as zeros.
-    if (!in_range || row0 >= p.M) continue;
-    // the store issued two chunks ago read this buffer: wait until it has been drained
-    if (lane == 0) tma_store_wait_read<1>();
-    __syncwarp();
-    uint8_t* ob = out_buf + (out_cnt & 1) * kChunkBytes;
-    ++out_cnt;
-    if constexpr (OUT_F32) {
+    if constexpr (!WIDE) {
+      if (!in_range || row0 >= p.M) continue;
+      // the store issued two chunks ago read this buffer: wait until it has been drained
+      if (lane == 0) tma_store_wait_read<1>();
+      __syncwarp();
+      ob = out_buf + (out_cnt & 1) * kChunkBytes;
+      ++out_cnt;
+      if constexpr (OUT_F32) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        *reinterpret_cast<float4*>(ob + sw64(lane, j)) =
-            make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-    } else {
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(ob + sw64(lane, j)) =
+              make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+      } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 q;
-        q.x = pack_bf16x2(r[8 * j], r[8 * j + 1]);
-        q.y = pack_bf16x2(r[8 * j + 2], r[8 * j + 3]);
-        q.z = pack_bf16x2(r[8 * j + 4], r[8 * j + 5]);
-        q.w = pack_bf16x2(r[8 * j + 6], r[8 * j + 7]);
-        *reinterpret_cast<uint4*>(ob + sw64(lane, j)) = q;
+        for (int j = 0; j < 4; ++j) {
+          uint4 q;
+          q.x = pack_bf16x2(r[8 * j], r[8 * j + 1]);
+          q.y = pack_bf16x2(r[8 * j + 2], r[8 * j + 3]);
+          q.z = pack_bf16x2(r[8 * j + 4], r[8 * j + 5]);
+          q.w = pack_bf16x2(r[8 * j + 6], r[8 * j + 7]);
+          *reinterpret_cast<uint4*>(ob + sw64(lane, j)) = q;
+        }
       }
-    }
-    fence_proxy_async_smem();
-    __syncwarp();
-    if (lane == 0) {
-      tma_store_4d(tm_out, ob, n0, row0, bz % p.batch_inner, bz / p.batch_inner);
-      tma_store_commit();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_4d(tm_out, ob, n0, row0, bz % p.batch_inner, bz / p.batch_inner);
+        tma_store_commit();
+      }
+    } else {
+      if (sub == 0) {
+        group_ok = in_range && row0 < p.M;
+        if (group_ok) {
+          // the store issued two groups ago read this 4 KB buffer: wait until it has been drained
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          ob = out_buf + (out_cnt & 1) * (2 * kChunkBytes);
+          ++out_cnt;
+        }
+      }
+      if (group_ok && in_range) {
+        // 128-byte rows, 128B swizzle: 16-byte piece jj of row r lives at r * 128 + ((jj ^ (r & 7)) << 4);
+        // this chunk fills pieces sub * 4 .. sub * 4 + 3 of the warp's 32 rows
+        uint8_t* rowp = ob + lane * 128;
+        const int x = lane & 7;
+        if constexpr (OUT_F32) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(rowp + (((sub * 4 + j) ^ x) << 4)) =
+                make_float4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 q;
+            q.x = pack_bf16x2(r[8 * j], r[8 * j + 1]);
+            q.y = pack_bf16x2(r[8 * j + 2], r[8 * j + 3]);
+            q.z = pack_bf16x2(r[8 * j + 4], r[8 * j + 5]);
+            q.w = pack_bf16x2(r[8 * j + 6], r[8 * j + 7]);
+            *reinterpret_cast<uint4*>(rowp + (((sub * 4 + j) ^ x) << 4)) = q;
+          }
+        }
+      }
+      if (sub == SUBS - 1 && group_ok) {
+        // columns of the group past N (second chunk out of range) are clipped by the TMA store
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(tm_out, ob, col_base + c0 * COLS, row0, bz % p.batch_inner, bz / p.batch_inner);
+          tma_store_commit();
+        }
+      }
     }
   }
 }
@@ -745,13 +806,14 @@ struct SmemLayout2 {
   static constexpr int kStageA = BM * BK * 2;   // this CTA's 128 rows of A
   static constexpr int kStageB = 128 * BK * 2;  // this CTA's half of the 256 W rows
   static constexpr int kStage = kStageA + kStageB;
-  static constexpr int kStages = RES ? 5 : 6;
-  static constexpr int kEpiBufs = RES ? kResRing + 1 : 2;  // per warp: residual ring used in place + two
-                                                           // half-size bf16 buffers, or 2 out
+  static constexpr int kStages = (RES || kWideStores) ? 5 : 6;
+  static constexpr int kEpiBufs = RES ? kResRing + 1 : (kWideStores ? 4 : 2);  // per warp (2 KB units): residual ring used in place
+                                                           // + two half-size bf16 buffers, or two 4 KB
+                                                           // buffers of 128-byte rows (wide stores)
   static constexpr int kResBars = RES ? kResRing : 2;   // per warp
   static constexpr int kEpiBytes = kEpiWarps * kEpiBufs * kChunkBytes;
   static constexpr int kBarBytes = 512;
-  static_assert((2 * (RES ? 5 : 6) + 4 + kEpiWarps * kResBars) * 8 + 4 <= kBarBytes, "barrier area");
+  static_assert((2 * kStages + 4 + kEpiWarps * kResBars) * 8 + 4 <= kBarBytes, "barrier area");
   static constexpr int kTotal = kStages * kStage + kEpiBytes + kBarBytes + 1024;
   static_assert(kTotal <= 232448, "shared memory budget exceeded");
 };
@@ -938,13 +1000,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
         epilogue_tile_res_ring(p, &tm_out, &tm_out2, t_row, mb, nb, quad, half, lane, rs, res_wait,
                                tempty_leader[acc]);
       } else if (p.out_f32) {
-        epilogue_tile_tma<BN, false, true>(p, &tm_out, &tm_res, t_row, bz, mb, nb, quad, half, lane, out_buf,
-                                           out_buf, res_full, out_cnt, res_issue, res_wait, tempty_leader[acc],
-                                           &tfull[acc], acc_ph, ln_rstd);
+        epilogue_tile_tma<BN, false, true, kWideStores>(p, &tm_out, &tm_res, t_row, bz, mb, nb, quad, half, lane, out_buf,
+                                                 out_buf, res_full, out_cnt, res_issue, res_wait,
+                                                 tempty_leader[acc], &tfull[acc], acc_ph, ln_rstd);
       } else {
-        epilogue_tile_tma<BN, false, false>(p, &tm_out, &tm_res, t_row, bz, mb, nb, quad, half, lane,
-                                            out_buf, out_buf, res_full, out_cnt, res_issue, res_wait,
-                                            tempty_leader[acc], &tfull[acc], acc_ph, ln_rstd);
+        epilogue_tile_tma<BN, false, false, kWideStores>(p, &tm_out, &tm_res, t_row, bz, mb, nb, quad, half, lane,
+                                                  out_buf, out_buf, res_full, out_cnt, res_issue, res_wait,
+                                                  tempty_leader[acc], &tfull[acc], acc_ph, ln_rstd);
       }
     }
     if (lane == 0) tma_store_wait<0>();
@@ -990,8 +1052,12 @@ int launch2(const dod_gemm_args& a, cudaStream_t stream) {
   }
   const bool out_f32 = a.out_dtype == DOD_F32;
   const int64_t n_out = a.act == DOD_ACT_SWIGLU ? a.n / 2 : a.n;
-  if (int rc = make_tmap_4d(&tm_out, a.out, out_f32 ? 4 : 2, bd.outer, bd.inner, a.m, n_out, bd.os_o, bd.is_o,
-                            a.ldo, 32, out_f32 ? 16 : 32, 64))
+  // residual epilogue: 64-byte rows (in-place ring); otherwise 128-byte rows (wide stores)
+  if (int rc = (RES || !kWideStores)
+                   ? make_tmap_4d(&tm_out, a.out, out_f32 ? 4 : 2, bd.outer, bd.inner, a.m, n_out, bd.os_o, bd.is_o, a.ldo,
+                                  32, out_f32 ? 16 : 32, 64)
+                   : make_tmap_4d(&tm_out, a.out, out_f32 ? 4 : 2, bd.outer, bd.inner, a.m, n_out, bd.os_o, bd.is_o,
+                                  a.ldo, 32, out_f32 ? 32 : 64, 128))
     return rc;
   if (RES) {
     if (int rc = make_tmap_2d(&tm_res, a.residual, 4, a.m, a.n, a.ldr, 32, 16, 64)) return rc;
