@@ -53,7 +53,7 @@ WORKLOAD = ("BASELINE configs[1]: DINOv2-B/14 detector (reference default ctor: 
 def _ncu_traffic():
     """DRAM bytes per GEMM launch (read + write) from the committed `ncu --set full` capture of one
     encoder layer (profiles/): average over its four GEMMs; None if the summary is not there."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_final2_traffic.json")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_final3_traffic.json")
     try:
         with open(path) as fh:
             return json.load(fh)["gemm"]["avg_dram_bytes_per_launch"]
@@ -85,8 +85,21 @@ class ClockSampler:
 
     def __init__(self, index):
         self.rows, self.proc, self.index = [], None, index
+        self.nvml, self.nvml_rows, self._stop = None, [], threading.Event()
 
     def start(self):
+        # NVML in a thread (a sample every ~5 ms: the timed region is a few hundred ms); the nvidia-smi loop
+        # (-lms 100, first line after ~0.3 s) is the fallback when pynvml cannot be loaded
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.nvml = (pynvml, h)
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -96,11 +109,40 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
+
+    def _poll(self):
+        pynvml, h = self.nvml
+        while not self._stop.is_set():
+            try:
+                self.nvml_rows.append((pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM),
+                                       pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM),
+                                       pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            bits = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20,
+                    "hw_thermal_slowdown": 0x40}
+            sm = [r[0] for r in self.nvml_rows]
+            reasons = sorted(n for n, b in bits.items() if any(r[2] & b for r in self.nvml_rows))
+            return {"sm_mhz": statistics.median(sm) if sm else None,
+                    "sm_max_mhz": max(r[1] for r in self.nvml_rows) if sm else None,
+                    "reasons": reasons, "samples": len(sm), "source": "nvml, 5 ms period over the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()

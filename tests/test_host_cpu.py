@@ -84,3 +84,34 @@ def test_forward_without_gpu_fails_loudly():
     model, _, _ = build_product_model("c1_small_std")
     with torch.no_grad(), pytest.raises(DodError):
         model(torch.rand(1, 3, 224, 224))
+
+
+def test_layernorm_fold_and_lora_merge_identities():
+    """The algebra behind the default bf16 inference packs (_engine.PackedLinear ln=..., _lin_parts merge=True),
+    checked in float64 on the CPU:
+      LN(h) W^T + b == rstd * (h W''^T) + (b + W beta)   with W'' = gamma (.) W minus its row means,
+      (W + alpha B A) x == W x + alpha B (A x)            (reference utils.py:68-70)."""
+    import torch
+    g = torch.Generator().manual_seed(0)
+    m, d, n, r = 37, 96, 40, 4
+    h = torch.randn(m, d, generator=g, dtype=torch.float64) * 3 + 1.5
+    w = torch.randn(n, d, generator=g, dtype=torch.float64)
+    b = torch.randn(n, generator=g, dtype=torch.float64)
+    gamma = 1 + 0.3 * torch.randn(d, generator=g, dtype=torch.float64)
+    beta = 0.2 * torch.randn(d, generator=g, dtype=torch.float64)
+    eps = 1e-6
+    ref = torch.nn.functional.layer_norm(h, (d,), gamma, beta, eps) @ w.t() + b
+    w2 = w * gamma[None, :]
+    w2 = w2 - w2.mean(dim=1, keepdim=True)
+    s1, s2 = h.sum(1), (h * h).sum(1)                     # what the producer GEMM's epilogue accumulates
+    mean = s1 / d
+    rstd = torch.rsqrt((s2 / d - mean * mean).clamp_min(0) + eps)
+    out = rstd[:, None] * (h @ w2.t()) + (b + w @ beta)
+    assert torch.allclose(out, ref, rtol=1e-9, atol=1e-9)
+
+    a_l = torch.randn(r, d, generator=g, dtype=torch.float64)
+    b_l = torch.randn(n, r, generator=g, dtype=torch.float64)
+    alpha = 0.7
+    x = torch.randn(m, d, generator=g, dtype=torch.float64)
+    assert torch.allclose(x @ (w + alpha * b_l @ a_l).t() + b, x @ w.t() + b + alpha * (x @ a_l.t()) @ b_l.t(),
+                          rtol=1e-10, atol=1e-10)
