@@ -153,10 +153,11 @@ def test_transpose(ops):
     assert torch.equal(ops.transpose(y), y.t())
 
 
-@pytest.mark.parametrize("r", [1, 2, 8, 24])
-def test_lowrank_wgrad_and_colsum(ops, r):
-    g = _g(r)
-    m, c = 3001, 777
+@pytest.mark.parametrize("c", [777, 776, 1024])        # 777: unaligned rows -> thread-per-column fallback kernel
+@pytest.mark.parametrize("r", [1, 2, 8, 12, 24, 40])
+def test_lowrank_wgrad_and_colsum(ops, r, c):
+    g = _g(r + c)
+    m = 3001
     big = _randn((m, c), g).bfloat16()
     small = torch.zeros((m, 64), dtype=torch.bfloat16, device="cuda")
     small[:, :r] = _randn((m, r), g).bfloat16()
