@@ -203,6 +203,15 @@ def test_eltwise_modes(ops):
     torch.nn.functional.gelu(z).backward(b)
     assert torch.allclose(ops.eltwise(ops.ELT_GELU_FWD, a, out_dtype=torch.float32), torch.nn.functional.gelu(a), atol=1e-6)
     assert torch.allclose(ops.eltwise(ops.ELT_GELU_BWD, b, a, out_dtype=torch.float32), z.grad, atol=1e-5)
+    # bf16 outputs use the one-MUFU tanh / ex2 forms: within bf16 rounding of the exact result
+    wide_a = a * 3.0
+    zz = wide_a.clone().requires_grad_(True)
+    torch.nn.functional.gelu(zz).backward(b)
+    out16 = ops.eltwise(ops.ELT_GELU_FWD, wide_a, out_dtype=torch.bfloat16).float()
+    ref16 = torch.nn.functional.gelu(wide_a)
+    assert ((out16 - ref16).abs() <= 2.0 ** -8 * ref16.abs() + 3e-4).all()
+    g16 = ops.eltwise(ops.ELT_GELU_BWD, b, wide_a, out_dtype=torch.bfloat16).float()
+    assert ((g16 - zz.grad).abs() <= 2.0 ** -8 * zz.grad.abs() + 6e-4 * b.abs() + 1e-6).all()
     relu = torch.relu(a)
     assert torch.equal(ops.eltwise(ops.ELT_RELU_BWD, b, relu, out_dtype=torch.float32), b * (relu > 0))
     sg = torch.sigmoid(a)
