@@ -43,9 +43,15 @@ constexpr int kSmemBytes = kTileBytes * (1 + 2 * kKVStages) + 256 + kXchgBytes +
 // raw MUFU.EX2 (flush-to-zero): exp2f() wraps it in a denormal-range test + two multiplies per
 // element, which doubled the issue slots of the softmax loop
 __device__ __forceinline__ float ex2_approx(float x) {
+#ifdef DOD_FMHA_NOEXP
+  // developer experiment (tools/build_variant.sh noexp attention.cu -DDOD_FMHA_NOEXP): wrong results, shows the
+  // kernel's time with the MUFU work removed
+  return fmaf(x, 0.001f, 1.0f);
+#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 
 #ifdef DOD_FMHA_TRACE

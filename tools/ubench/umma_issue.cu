@@ -138,5 +138,10 @@ int main() {
     run<0, 256>("SS M128 N256 K16", grid, d);
     run<1, 64>("TS M128 N64 K16 (PV)", grid, d);
   }
+  // two CTAs per SM issuing at once (the FMHA kernel's residency): does the tensor pipe serialise them?
+  printf("--- 296 CTAs (2 per SM)\n");
+  run<0, 64>("SS M128 N64 K16", 296, d);
+  run<0, 128>("SS M128 N128 K16", 296, d);
+  run<1, 64>("TS M128 N64 K16 (PV)", 296, d);
   return 0;
 }
