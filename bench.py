@@ -368,10 +368,11 @@ def run_ours(args):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        rate, times = cpu_forward_rate(model.state_dict(), 2, 3, threads)
+        # bounded sample: 8 forwards of 4 images are ~12 s of CPU work on the box's 16 cores
+        rate, times = cpu_forward_rate(model.state_dict(), 4, 8, threads)
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"2 of {BATCH} images per step, 3 timed forwards (fp32 CPU oracle of the reference), "
-                         f"median {statistics.median(times):.2f} s"}
+               "sample": f"4 of {BATCH} images per step, 8 timed forwards (fp32 CPU oracle of the reference), "
+                         f"median {statistics.median(times):.2f} s, total {sum(times):.1f} s"}
     h2d = host.numel() * host.element_size()
     d2h = sum(v.numel() * v.element_size() for v in out_host.values())
     line = {
