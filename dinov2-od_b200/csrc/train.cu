@@ -198,11 +198,16 @@ layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dt, const float* __rest
                      float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
                      int64_t rows, int d, float eps) {
   const int lane = threadIdx.x & 31;
-  const int64_t row = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const int nvec = d >> 2;
-  // per-CTA partial dgamma/dbeta in shared memory would need d floats x2; rows are few when these
-  // are requested (decoder LNs), so plain atomics per row are fine there.
-  if (row >= rows) return;
+  // dgamma / dbeta (decoder LayerNorms): per-CTA partial sums in shared memory, one global atomic per column
+  // and CTA at the end.  One global atomic per element and row (1600 rows x 768 columns x 2 on the same 1536
+  // addresses) serialised in L2 and made these small launches as slow as the [43840, 1024] ones.
+  extern __shared__ float s_part[];  // [2][d] when dgamma != nullptr
+  if (dgamma) {
+    for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) s_part[i] = 0.f;
+    __syncthreads();
+  }
+  for (int64_t row = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5); row < rows; row += int64_t(gridDim.x) * 8) {
   float4 xv[kLnMaxVec], gv[kLnMaxVec];
   float s = 0.f;
 #pragma unroll
@@ -230,20 +235,25 @@ layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dt, const float* __rest
     const int c = lane + i * 32;
     if (c < nvec) {
       xv[i].x *= rstd; xv[i].y *= rstd; xv[i].z *= rstd; xv[i].w *= rstd;  // xhat
+      // one 16-byte (f32) / 8-byte (bf16) load per lane: four scalar loads per lane moved 2-4 bytes per
+      // instruction and held the kernel at 3.8 TB/s
       float4 dyv;
-      dyv.x = ldv(dy, row * d + c * 4 + 0, dy_dt);
-      dyv.y = ldv(dy, row * d + c * 4 + 1, dy_dt);
-      dyv.z = ldv(dy, row * d + c * 4 + 2, dy_dt);
-      dyv.w = ldv(dy, row * d + c * 4 + 3, dy_dt);
+      if (dy_dt == DOD_F32) {
+        dyv = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy) + row * d + c * 4);
+      } else {
+        const uint2 rw = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dy) + row * d + c * 4);
+        dyv = make_float4(__uint_as_float(rw.x << 16), __uint_as_float(rw.x & 0xffff0000u),
+                          __uint_as_float(rw.y << 16), __uint_as_float(rw.y & 0xffff0000u));
+      }
       if (dgamma) {
-        atomicAdd(dgamma + c * 4 + 0, dyv.x * xv[i].x);
-        atomicAdd(dgamma + c * 4 + 1, dyv.y * xv[i].y);
-        atomicAdd(dgamma + c * 4 + 2, dyv.z * xv[i].z);
-        atomicAdd(dgamma + c * 4 + 3, dyv.w * xv[i].w);
-        atomicAdd(dbeta + c * 4 + 0, dyv.x);
-        atomicAdd(dbeta + c * 4 + 1, dyv.y);
-        atomicAdd(dbeta + c * 4 + 2, dyv.z);
-        atomicAdd(dbeta + c * 4 + 3, dyv.w);
+        atomicAdd(s_part + c * 4 + 0, dyv.x * xv[i].x);
+        atomicAdd(s_part + c * 4 + 1, dyv.y * xv[i].y);
+        atomicAdd(s_part + c * 4 + 2, dyv.z * xv[i].z);
+        atomicAdd(s_part + c * 4 + 3, dyv.w * xv[i].w);
+        atomicAdd(s_part + d + c * 4 + 0, dyv.x);
+        atomicAdd(s_part + d + c * 4 + 1, dyv.y);
+        atomicAdd(s_part + d + c * 4 + 2, dyv.z);
+        atomicAdd(s_part + d + c * 4 + 3, dyv.w);
       }
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
       gv[i] = make_float4(dyv.x * g.x, dyv.y * g.y, dyv.z * g.z, dyv.w * g.w);
@@ -266,6 +276,14 @@ layernorm_bwd_kernel(const void* __restrict__ dy, int dy_dt, const float* __rest
         o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
       }
       *reinterpret_cast<float4*>(dx + row * d + c * 4) = o;
+    }
+  }
+  }  // rows of this warp
+  if (dgamma) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < d; i += blockDim.x) {
+      atomicAdd(dgamma + i, s_part[i]);
+      atomicAdd(dbeta + i, s_part[d + i]);
     }
   }
 }
@@ -700,7 +718,14 @@ extern "C" int32_t dod_layernorm_bwd(const dod_layernorm_bwd_args* a, dod_stream
   DOD_REQUIRE(a->rows > 0 && a->d > 0 && a->d % 4 == 0 && a->d <= kLnMaxVec * 128,
               "dod_layernorm_bwd: d must be a multiple of 4 and <= %d", kLnMaxVec * 128);
   DOD_REQUIRE((a->dgamma == nullptr) == (a->dbeta == nullptr), "dod_layernorm_bwd: dgamma/dbeta go together");
-  layernorm_bwd_kernel<<<unsigned((a->rows + 7) / 8), 256, 0, stream>>>(
+  DOD_REQUIRE((uintptr_t(a->dy) & 15) == 0 && (uintptr_t(a->x) & 15) == 0 && (uintptr_t(a->dx) & 15) == 0 &&
+                  (!a->dres || (uintptr_t(a->dres) & 15) == 0),
+              "dod_layernorm_bwd: dy / x / dx / dres must be 16-byte aligned");
+  // with dgamma / dbeta: few persistent CTAs (each ends with 2 d global atomics); without: one row per warp
+  const int64_t ctas = (a->rows + 7) / 8;
+  const unsigned grid = unsigned(a->dgamma && ctas > 148 ? 148 : ctas);
+  const size_t smem = a->dgamma ? size_t(2 * a->d) * sizeof(float) : 0;
+  layernorm_bwd_kernel<<<grid, 256, smem, stream>>>(
       a->dy, a->dy_dtype, a->x, a->gamma, a->dres, a->dx, a->dgamma, a->dbeta, a->rows, int(a->d), a->eps);
   int rc = check_cuda(cudaGetLastError(), "layernorm_bwd_kernel launch");
   if (rc == 0) count_launch();
