@@ -19,39 +19,26 @@ namespace {
 constexpr int kP = 14;
 constexpr int kK = 3 * kP * kP;  // 588
 
-// grid (patch-row, batch); block 256.  The gw patches of one patch row are gw * kpad CONTIGUOUS bf16 of the
-// output: the 42 image row segments are read coalesced, converted into that layout in shared memory and
-// written out with 16-byte stores (2-byte stores scattered in 28-byte runs held the first version at 2.5 TB/s).
-// Falls back to direct stores when the staging tile does not fit (very wide images).
-template <bool STAGE>
+// grid (patch-row, batch); block 256.  Each image row segment is read coalesced.
 __global__ void __launch_bounds__(256)
 patchify_kernel(const float* __restrict__ pix, __nv_bfloat16* __restrict__ out, int H, int W,
                 int gh, int gw, int kpad) {
-  extern __shared__ __align__(16) uint8_t stage_raw[];
-  __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(stage_raw);  // [gw][kpad]
   const int py = blockIdx.x, b = blockIdx.y;
   const int wuse = gw * kP;
   const int64_t row0 = (int64_t(b) * gh + py) * gw;
-  __nv_bfloat16* dst = STAGE ? stage : out + row0 * kpad;
   for (int ci = 0; ci < 3 * kP; ++ci) {
     const int c = ci / kP, i = ci % kP;
     const float* src = pix + ((int64_t(b) * 3 + c) * H + (py * kP + i)) * W;
     for (int x = threadIdx.x; x < wuse; x += blockDim.x) {
       const int px = x / kP, j = x - px * kP;
-      dst[px * kpad + c * (kP * kP) + i * kP + j] = __float2bfloat16_rn(__ldg(src + x));
+      out[(row0 + px) * kpad + c * (kP * kP) + i * kP + j] = __float2bfloat16_rn(src[x]);
     }
   }
   // zero the K padding so that 0-weights never meet NaN garbage
   const int padw = kpad - kK;
   for (int t = threadIdx.x; t < gw * padw; t += blockDim.x) {
     const int px = t / padw, k = kK + t % padw;
-    dst[px * kpad + k] = __float2bfloat16_rn(0.f);
-  }
-  if constexpr (STAGE) {
-    __syncthreads();
-    const uint4* s4 = reinterpret_cast<const uint4*>(stage);
-    uint4* o4 = reinterpret_cast<uint4*>(out + row0 * kpad);  // kpad % 8 == 0: 16-byte aligned
-    for (int t = threadIdx.x; t < gw * kpad / 8; t += blockDim.x) o4[t] = s4[t];
+    out[(row0 + px) * kpad + k] = __float2bfloat16_rn(0.f);
   }
 }
 
@@ -148,23 +135,9 @@ extern "C" int32_t dod_patchify14(const dod_patchify_args* a, dod_stream_t strea
         reinterpret_cast<const uint8_t*>(a->pixels), reinterpret_cast<__nv_bfloat16*>(a->patches),
         int(a->height), int(a->width), gh, gw, int(a->kpad));
   else
-  {
-    const size_t stage_bytes = size_t(gw) * a->kpad * 2;
-    if (stage_bytes <= 96 * 1024 && (uintptr_t(a->patches) & 15) == 0) {
-      static bool attr_set = false;
-      if (!attr_set) {
-        DOD_CUDA_OK(cudaFuncSetAttribute(patchify_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr_set = true;
-      }
-      patchify_kernel<true><<<dim3(gh, unsigned(a->batch)), 256, stage_bytes, stream>>>(
-          reinterpret_cast<const float*>(a->pixels), reinterpret_cast<__nv_bfloat16*>(a->patches),
-          int(a->height), int(a->width), gh, gw, int(a->kpad));
-    } else {
-      patchify_kernel<false><<<dim3(gh, unsigned(a->batch)), 256, 0, stream>>>(
-          reinterpret_cast<const float*>(a->pixels), reinterpret_cast<__nv_bfloat16*>(a->patches),
-          int(a->height), int(a->width), gh, gw, int(a->kpad));
-    }
-  }
+    patchify_kernel<<<dim3(gh, unsigned(a->batch)), 256, 0, stream>>>(
+        reinterpret_cast<const float*>(a->pixels), reinterpret_cast<__nv_bfloat16*>(a->patches),
+        int(a->height), int(a->width), gh, gw, int(a->kpad));
   int rc = check_cuda(cudaGetLastError(), "patchify_kernel launch");
   if (rc) return rc;
   count_launch();
