@@ -43,7 +43,27 @@ __device__ __forceinline__ void st1<__nv_bfloat16>(__nv_bfloat16* p, float v) {
 // scores by thread per (query, key) pair, softmax by warp per row, output by thread per (query, channel).
 // The key-per-thread kernel below leaves 80 % of its threads idle at Lk = 50 (185 us per decoder layer at
 // batch 64; this one: a few microseconds).
-template <typename T>
+// 8 consecutive elements of a row -> fp32 (16-byte load for bf16 when VEC, else scalar loads)
+template <typename T, bool VEC>
+__device__ __forceinline__ void ld_row8(const T* p, float (&v)[8]) {
+  if constexpr (VEC && sizeof(T) == 2) {
+    const uint4 r = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = ld1(p + i);
+  }
+}
+
+// VEC: dh % 8 == 0 and 16-byte-aligned rows.  Scores and outputs are register-tiled (4 queries x 2 keys,
+// 4 queries x 1 channel per thread): the first version read two shared-memory words per FMA and spent 100 us
+// per decoder layer at batch 64 on 0.5 GFLOP.
+template <typename T, bool VEC>
 __global__ void __launch_bounds__(kMhaThreads)
 mha_tiny_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v,
                 T* __restrict__ out, int lq, int lk, int dh, int64_t ldq, int64_t ldk, int64_t ldv,
@@ -56,23 +76,66 @@ mha_tiny_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __res
   float* sp = sv + lk * pitch;     // [lq][lkp]
   const int h = blockIdx.x, b = blockIdx.y;
   const int t = threadIdx.x;
-  for (int i = t; i < lq * dh; i += kMhaThreads) {
-    const int r = i / dh, d = i - r * dh;
-    sq[r * pitch + d] = ld1(q + (int64_t(b) * lq + r) * ldq + h * dh + d) * scale;
-  }
-  for (int i = t; i < lk * dh; i += kMhaThreads) {
-    const int r = i / dh, d = i - r * dh;
-    sk[r * pitch + d] = ld1(k + (int64_t(b) * lk + r) * ldk + h * dh + d);
-    sv[r * pitch + d] = ld1(v + (int64_t(b) * lk + r) * ldv + h * dh + d);
+  if constexpr (VEC) {
+    const int dv = dh >> 3;
+    for (int i = t; i < lq * dv; i += kMhaThreads) {
+      const int r = i / dv, c = (i - r * dv) << 3;
+      float x[8];
+      ld_row8<T, true>(q + (int64_t(b) * lq + r) * ldq + h * dh + c, x);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sq[r * pitch + c + e] = x[e] * scale;
+    }
+    for (int i = t; i < lk * dv; i += kMhaThreads) {
+      const int r = i / dv, c = (i - r * dv) << 3;
+      float x[8], y[8];
+      ld_row8<T, true>(k + (int64_t(b) * lk + r) * ldk + h * dh + c, x);
+      ld_row8<T, true>(v + (int64_t(b) * lk + r) * ldv + h * dh + c, y);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        sk[r * pitch + c + e] = x[e];
+        sv[r * pitch + c + e] = y[e];
+      }
+    }
+  } else {
+    for (int i = t; i < lq * dh; i += kMhaThreads) {
+      const int r = i / dh, d = i - r * dh;
+      sq[r * pitch + d] = ld1(q + (int64_t(b) * lq + r) * ldq + h * dh + d) * scale;
+    }
+    for (int i = t; i < lk * dh; i += kMhaThreads) {
+      const int r = i / dh, d = i - r * dh;
+      sk[r * pitch + d] = ld1(k + (int64_t(b) * lk + r) * ldk + h * dh + d);
+      sv[r * pitch + d] = ld1(v + (int64_t(b) * lk + r) * ldv + h * dh + d);
+    }
   }
   __syncthreads();
-  for (int i = t; i < lq * lk; i += kMhaThreads) {
-    const int qi = i / lk, ki = i - qi * lk;  // consecutive threads: consecutive keys of one query
-    const float* a = sq + qi * pitch;
-    const float* c = sk + ki * pitch;
-    float acc = 0.f;
-    for (int d = 0; d < dh; ++d) acc = fmaf(a[d], c[d], acc);
-    sp[qi * lkp + ki] = acc;
+  // scores: thread = 4 queries x 2 keys (keys kb and kb + nkb: consecutive threads read consecutive K rows,
+  // odd pitch -> no bank conflicts; the Q words are warp-wide broadcasts)
+  const int nqb = (lq + 3) >> 2, nkb = (lk + 1) >> 1;
+  for (int item = t; item < nqb * nkb; item += kMhaThreads) {
+    const int qb = item / nkb, kb = item - qb * nkb;
+    const int q0 = qb << 2, k0 = kb, k1 = kb + nkb;
+    const float* a0 = sq + min(q0, lq - 1) * pitch;
+    const float* a1 = sq + min(q0 + 1, lq - 1) * pitch;
+    const float* a2 = sq + min(q0 + 2, lq - 1) * pitch;
+    const float* a3 = sq + min(q0 + 3, lq - 1) * pitch;
+    const float* c0 = sk + k0 * pitch;
+    const float* c1 = sk + min(k1, lk - 1) * pitch;
+    float acc[4][2] = {};
+    for (int d = 0; d < dh; ++d) {
+      const float x0 = c0[d], x1 = c1[d];
+      const float y0 = a0[d], y1 = a1[d], y2 = a2[d], y3 = a3[d];
+      acc[0][0] = fmaf(y0, x0, acc[0][0]); acc[0][1] = fmaf(y0, x1, acc[0][1]);
+      acc[1][0] = fmaf(y1, x0, acc[1][0]); acc[1][1] = fmaf(y1, x1, acc[1][1]);
+      acc[2][0] = fmaf(y2, x0, acc[2][0]); acc[2][1] = fmaf(y2, x1, acc[2][1]);
+      acc[3][0] = fmaf(y3, x0, acc[3][0]); acc[3][1] = fmaf(y3, x1, acc[3][1]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (q0 + i < lq) {
+        sp[(q0 + i) * lkp + k0] = acc[i][0];
+        if (k1 < lk) sp[(q0 + i) * lkp + k1] = acc[i][1];
+      }
+    }
   }
   __syncthreads();
   const int warp = t >> 5, lane = t & 31;
@@ -91,12 +154,27 @@ mha_tiny_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __res
     for (int j = lane; j < lk; j += 32) row[j] *= inv;
   }
   __syncthreads();
-  for (int i = t; i < lq * dh; i += kMhaThreads) {
-    const int qi = i / dh, d = i - qi * dh;   // consecutive threads: consecutive channels
-    const float* pr = sp + qi * lkp;
-    float acc = 0.f;
-    for (int j = 0; j < lk; ++j) acc = fmaf(pr[j], sv[j * pitch + d], acc);
-    st1(out + (int64_t(b) * lq + qi) * ldo + h * dh + d, acc);
+  // output: thread = 4 queries x 1 channel (consecutive threads: consecutive channels of V, P words broadcast)
+  for (int item = t; item < nqb * dh; item += kMhaThreads) {
+    const int qb = item / dh, d = item - qb * dh;
+    const int q0 = qb << 2;
+    const float* p0 = sp + min(q0, lq - 1) * lkp;
+    const float* p1 = sp + min(q0 + 1, lq - 1) * lkp;
+    const float* p2 = sp + min(q0 + 2, lq - 1) * lkp;
+    const float* p3 = sp + min(q0 + 3, lq - 1) * lkp;
+    float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+    for (int j = 0; j < lk; ++j) {
+      const float x = sv[j * pitch + d];
+      o0 = fmaf(p0[j], x, o0);
+      o1 = fmaf(p1[j], x, o1);
+      o2 = fmaf(p2[j], x, o2);
+      o3 = fmaf(p3[j], x, o3);
+    }
+    T* op = out + (int64_t(b) * lq + q0) * ldo + h * dh + d;
+    st1(op, o0);
+    if (q0 + 1 < lq) st1(op + ldo, o1);
+    if (q0 + 2 < lq) st1(op + 2 * ldo, o2);
+    if (q0 + 3 < lq) st1(op + 3 * ldo, o3);
   }
 }
 
@@ -313,19 +391,22 @@ extern "C" int32_t dod_mha_small(const dod_mha_small_args* a, dod_stream_t strea
     const size_t tiny = sizeof(float) * (size_t(a->lq + 2 * a->lk) * pitch + size_t(a->lq) * lkp);
     if (tiny <= 200 * 1024) {
       dim3 grid(unsigned(a->heads), unsigned(a->batch));
+      const bool vec = a->dtype == DOD_BF16 && a->head_dim % 8 == 0 && a->ldq % 8 == 0 && a->ldk % 8 == 0 &&
+                       a->ldv % 8 == 0 && ((uintptr_t(a->q) | uintptr_t(a->k) | uintptr_t(a->v)) & 15) == 0;
+#define DOD_MHA_TINY(T, VEC)                                                                                    \
+  {                                                                                                             \
+    auto kern = mha_tiny_kernel<T, VEC>;                                                                        \
+    DOD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));           \
+    kern<<<grid, kMhaThreads, tiny, stream>>>((const T*)a->q, (const T*)a->k, (const T*)a->v, (T*)a->out,      \
+                                              int(a->lq), int(a->lk), int(a->head_dim), a->ldq, a->ldk, a->ldv, \
+                                              a->ldo, a->scale);                                                \
+  }
       if (a->dtype == DOD_BF16) {
-        auto kern = mha_tiny_kernel<__nv_bfloat16>;
-        DOD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        kern<<<grid, kMhaThreads, tiny, stream>>>((const __nv_bfloat16*)a->q, (const __nv_bfloat16*)a->k,
-                                                 (const __nv_bfloat16*)a->v, (__nv_bfloat16*)a->out, int(a->lq),
-                                                 int(a->lk), int(a->head_dim), a->ldq, a->ldk, a->ldv, a->ldo, a->scale);
+        if (vec) DOD_MHA_TINY(__nv_bfloat16, true) else DOD_MHA_TINY(__nv_bfloat16, false)
       } else {
-        auto kern = mha_tiny_kernel<float>;
-        DOD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        kern<<<grid, kMhaThreads, tiny, stream>>>((const float*)a->q, (const float*)a->k, (const float*)a->v,
-                                                 (float*)a->out, int(a->lq), int(a->lk), int(a->head_dim), a->ldq,
-                                                 a->ldk, a->ldv, a->ldo, a->scale);
+        DOD_MHA_TINY(float, false)
       }
+#undef DOD_MHA_TINY
       int rc = check_cuda(cudaGetLastError(), "mha_tiny_kernel launch");
       if (rc == 0) count_launch();
       return rc;
