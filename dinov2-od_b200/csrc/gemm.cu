@@ -23,6 +23,14 @@
 //     registers: 32 lanes x 16 B scattered over 32 rows per instruction made the
 //     K=768 GEMMs epilogue-bound at 16-43 % tensor-pipe utilisation, see
 //     profiles/r01_summary.md.)
+//   * CTA-pair kernel (gemm2_kernel, M >= 512 and N >= 256): without a residual the warp stores PAIRS of
+//     adjacent chunks as one 4 KB box of 128-byte rows; with the fp32 residual it runs an in-place ring of
+//     three chunk buffers per warp (TMA load -> add -> TMA store from the same buffer) that is filled two
+//     chunks ahead across tile boundaries.
+//   * LayerNorm folded across two GEMMs (include/dod.h): the residual epilogue can also emit bf16(out) and
+//     per-row partial sums of out / out^2 (producer); any TMA-store epilogue can multiply the accumulator
+//     by a per-row scale loaded one tile ahead (consumer: rstd, with gamma and the mean removal folded
+//     into the weights).
 //   * the patch-embedding row map (patch_rows > 0) cannot be expressed as a TMA
 //     box and keeps the direct register -> global path (0.4 % of the FLOPs).
 //
