@@ -71,6 +71,7 @@ struct GemmParams {
   int patch_rows;
   int direct;  // 1: register -> global epilogue (patch rows / shapes TMA cannot store)
   int a_trans, w_trans;  // operand stored [K, M] / [K, N]: MN-major smem tiles (64-column blocks 8 KB apart)
+  int w_shared;          // batched problem whose W (and residual) is the same for every batch entry
   // LayerNorm folded across two GEMMs (include/dod.h): producer outputs / consumer inputs
   __nv_bfloat16* out2;
   int64_t ldo2;
@@ -405,13 +406,15 @@ struct ResStream {
   uint8_t* buf;    // kResRing chunk buffers of this warp
   uint8_t* buf16;  // two half-chunk buffers (bf16 copy)
   uint64_t* bars;  // kResRing full barriers of this warp
-  int tile, c, num_tiles, num_pairs, tiles_n, rank, half;
+  int tile, c, num_tiles, num_pairs, tiles_n, tiles_per_batch, rank, half;
   int row0, col_base;
   uint32_t issued;
 
+  // the residual is shared by every batch entry (position embedding of the patch GEMM): rows within the batch
   __device__ __forceinline__ void locate(int quad) {
-    row0 = ((tile / tiles_n) * 2 + rank) * BM + quad * 32;
-    col_base = (tile % tiles_n) * 256;
+    const int tl = tile % tiles_per_batch;
+    row0 = ((tl / tiles_n) * 2 + rank) * BM + quad * 32;
+    col_base = (tl % tiles_n) * 256;
   }
   // whole warp calls; lane 0 issues the load of the next chunk of the stream
   __device__ __forceinline__ void issue(int lane, int quad) {
@@ -432,7 +435,7 @@ struct ResStream {
 };
 
 __device__ __forceinline__ void epilogue_tile_res_ring(const GemmParams& p, const CUtensorMap* tm_out,
-                                                       const CUtensorMap* tm_out2, uint32_t t_row, int mb, int nb, int quad, int half,
+                                                       const CUtensorMap* tm_out2, uint32_t t_row, int bz, int mb, int nb, int quad, int half,
                                                        int lane, ResStream& rs, uint32_t& res_wait,
                                                        uint32_t tempty_addr) {
   constexpr int COLS = 16, NCH = 256 / COLS;
@@ -515,7 +518,7 @@ __device__ __forceinline__ void epilogue_tile_res_ring(const GemmParams& p, cons
     __syncwarp();
     if (lane == 0) {
       if (in_range && row0 < p.M) {
-        tma_store_4d(tm_out, rb, n0, row0, 0, 0);
+        tma_store_4d(tm_out, rb, n0, row0, bz % p.batch_inner, bz / p.batch_inner);
         if (p.out2 != nullptr) tma_store_2d(tm_out2, hb, n0, row0);
       }
       tma_store_commit();  // one group per chunk (possibly empty) keeps the wait_group arithmetic uniform
@@ -905,6 +908,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
           if (rank == 0) mbar_expect_tx(&full[s], 2 * L::kStage);  // bytes of both CTAs
           if (kb < p.K1blocks) {
             const int bi = bz % p.batch_inner, bo = bz / p.batch_inner;
+            const int wbi = p.w_shared ? 0 : bi, wbo = p.w_shared ? 0 : bo;
             if (TRANS && p.a_trans) {
               tma_load_4d_2sm(sa, &tm_a, full_leader, row_a, kb * BK, bi, bo);
               tma_load_4d_2sm(sa + kMnBlockBytes, &tm_a, full_leader, row_a + 64, kb * BK, bi, bo);
@@ -912,10 +916,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
               tma_load_4d_2sm(sa, &tm_a, full_leader, kb * BK, row_a, bi, bo);
             }
             if (TRANS && p.w_trans) {
-              tma_load_4d_2sm(sb, &tm_w, full_leader, row_w, kb * BK, bi, bo);
-              tma_load_4d_2sm(sb + kMnBlockBytes, &tm_w, full_leader, row_w + 64, kb * BK, bi, bo);
+              tma_load_4d_2sm(sb, &tm_w, full_leader, row_w, kb * BK, wbi, wbo);
+              tma_load_4d_2sm(sb + kMnBlockBytes, &tm_w, full_leader, row_w + 64, kb * BK, wbi, wbo);
             } else {
-              tma_load_4d_2sm(sb, &tm_w, full_leader, kb * BK, row_w, bi, bo);
+              tma_load_4d_2sm(sb, &tm_w, full_leader, kb * BK, row_w, wbi, wbo);
             }
           } else {
             tma_load_3d_2sm(sa, &tm_a2, full_leader, (kb - p.K1blocks) * BK, row_a, 0);
@@ -981,6 +985,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
       rs.num_tiles = num_tiles;
       rs.num_pairs = num_pairs;
       rs.tiles_n = p.tiles_n;
+      rs.tiles_per_batch = tiles_per_batch;
       rs.rank = int(rank);
       rs.half = half;
       rs.issued = 0;
@@ -1005,7 +1010,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
       if constexpr (RES) {
         mbar_wait(&tfull[acc], acc_ph);
         tc_fence_after();
-        epilogue_tile_res_ring(p, &tm_out, &tm_out2, t_row, mb, nb, quad, half, lane, rs, res_wait,
+        epilogue_tile_res_ring(p, &tm_out, &tm_out2, t_row, bz, mb, nb, quad, half, lane, rs, res_wait,
                                tempty_leader[acc]);
       } else if (p.out_f32) {
         epilogue_tile_tma<BN, false, true, kWideStores>(p, &tm_out, &tm_res, t_row, bz, mb, nb, quad, half, lane, out_buf,
@@ -1048,8 +1053,12 @@ int launch2(const dod_gemm_args& a, cudaStream_t stream) {
   if (int rc = a.a_trans ? make_tmap_4d(&tm_a, a.a, 2, bd.outer, bd.inner, a.k, a.m, bd.os_a, bd.is_a, a.lda, BK, 64, 128)
                          : make_tmap_4d(&tm_a, a.a, 2, bd.outer, bd.inner, a.m, a.k, bd.os_a, bd.is_a, a.lda, 128, BK, 128))
     return rc;
-  if (int rc = a.w_trans ? make_tmap_4d(&tm_w, a.w, 2, bd.outer, bd.inner, a.k, a.n, bd.os_w, bd.is_w, a.ldw, BK, 64, 128)
-                         : make_tmap_4d(&tm_w, a.w, 2, bd.outer, bd.inner, a.n, a.k, bd.os_w, bd.is_w, a.ldw, 128, BK, 128))
+  // batch_stride_w == 0 on a batched problem: one W (and one residual) for every batch entry
+  const bool w_shared = a.batch > 1 && a.batch_stride_w == 0;
+  const uint64_t w_outer = w_shared ? 1 : bd.outer, w_inner = w_shared ? 1 : bd.inner;
+  const uint64_t w_os = w_shared ? uint64_t(a.n) * a.ldw : bd.os_w, w_is = w_shared ? uint64_t(a.n) * a.ldw : bd.is_w;
+  if (int rc = a.w_trans ? make_tmap_4d(&tm_w, a.w, 2, w_outer, w_inner, a.k, a.n, w_os, w_is, a.ldw, BK, 64, 128)
+                         : make_tmap_4d(&tm_w, a.w, 2, w_outer, w_inner, a.n, a.k, w_os, w_is, a.ldw, 128, BK, 128))
     return rc;
   if (a.a2) {
     if (int rc = make_tmap_3d(&tm_a2, a.a2, 2, 1, a.m, a.k2, uint64_t(a.m) * a.lda2, a.lda2, 128, BK, 128)) return rc;
@@ -1097,6 +1106,7 @@ int launch2(const dod_gemm_args& a, cudaStream_t stream) {
   p.a_trans = a.a_trans;
   p.w_trans = a.w_trans;
   fill_ln_params(p, a);
+  p.w_shared = w_shared ? 1 : 0;
   const int tiles = p.tiles_m * p.tiles_n * p.batch;
   const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
   gemm2_kernel<RES, TRANS><<<2 * pairs, kThreads, L::kTotal, stream>>>(tm_a, tm_w, tm_a2, tm_w2, tm_out, tm_res,
@@ -1164,6 +1174,7 @@ int launch(const dod_gemm_args& a, cudaStream_t stream, bool direct) {
   p.a_trans = a.a_trans;
   p.w_trans = a.w_trans;
   fill_ln_params(p, a);
+  p.w_shared = 0;
   const int tiles = p.tiles_m * p.tiles_n * p.batch;
   const int grid = tiles < num_sms() ? tiles : num_sms();
   gemm_kernel<BN, RES, TRANS><<<grid, kThreads, L::kTotal, stream>>>(tm_a, tm_w, tm_a2, tm_w2, tm_out, tm_res, p);
@@ -1260,11 +1271,19 @@ extern "C" int32_t dod_gemm_bf16(const dod_gemm_args* a, dod_stream_t stream_) {
                 "dod_gemm_bf16: batched problems take no residual / second K segment / patch rows");
   }
   if (a->batch > 1) {
-    DOD_REQUIRE(!a->residual && !a->a2 && a->patch_rows == 0,
-                "dod_gemm_bf16: batched problems take no residual / second K segment / patch rows");
+    // batch_stride_w == 0: W -- and the fp32 residual, if any -- is shared by every batch entry (the patch
+    // embedding: one GEMM per image so that its token rows form a TMA box).  CTA-pair kernel only.
+    const bool shared = a->batch_stride_w == 0;
+    if (shared)
+      DOD_REQUIRE(a->m >= 512 && a->n >= 256 && a->batch_inner <= 1 && !a->a_trans && !a->w_trans &&
+                      (!a->residual || a->out_dtype == DOD_F32) && use_pair_kernel(),
+                  "dod_gemm_bf16: a shared W (batch_stride_w == 0) needs m >= 512, n >= 256, one batch level");
+    DOD_REQUIRE((shared || !a->residual) && !a->a2 && a->patch_rows == 0,
+                "dod_gemm_bf16: batched problems take no second K segment / patch rows, and a residual only "
+                "together with a shared W");
     DOD_REQUIRE(a->batch_stride_a % 8 == 0 && a->batch_stride_w % 8 == 0 &&
                     a->batch_stride_out % (a->out_dtype == DOD_F32 ? 4 : 8) == 0 &&
-                    a->batch_stride_a > 0 && a->batch_stride_w > 0 && a->batch_stride_out > 0,
+                    a->batch_stride_a > 0 && a->batch_stride_w >= 0 && a->batch_stride_out > 0,
                 "dod_gemm_bf16: batch strides must be positive multiples of 16 bytes");
     DOD_REQUIRE(a->batch * (a->batch_inner > 1 ? a->batch_inner : 1) * ((a->m + 127) / 128) *
                         ((a->n + 63) / 64) < (1ll << 31),

@@ -302,6 +302,10 @@ def backbone_forward(pack: BackbonePack, pixel_values, final_norm=True):
         # fp32 mode: im2col once more in full precision (bf16 patches would cost 3 digits)
         patches = _patchify_f32(px, gh, gw)
         pack.patch(patches, residual=pos, out=x, patch_rows=p)
+    elif p >= 512 and b > 1:
+        # one GEMM per image inside ONE launch (W and the position embedding shared): an image's patch rows
+        # x[i*N + 1 : (i+1)*N] are a TMA box, so the CTA-pair kernel with its TMA epilogue applies
+        ops.gemm_per_image(patches, pack.patch.w, pack.patch.bias, pos[1:], x[1:], b, n * d)
     else:
         ops.gemm(patches, pack.patch.w, pack.patch.bias, residual=pos, out=x, patch_rows=p)
     scale = 1.0 / math.sqrt(64.0)

@@ -338,6 +338,23 @@ def counter_add(counters, delta=1):
     _dod.call("dod_counter_add", _stream(counters), counters=counters, n=counters.numel(), delta=delta)
 
 
+def gemm_per_image(a, w, bias, residual, out, batch, out_batch_stride):
+    """batch GEMMs  out_i = residual + a_i @ w.T + bias  that share w and the fp32 residual: a [batch * rows, K]
+    (image i = rows i * rows ...), out = 2-D f32 view starting at image 0's first output row, image i's rows start
+    out_batch_stride elements later.  rows >= 512 (CTA-pair kernel); rows past `rows` of an image are never written."""
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and out.dtype == torch.float32
+    assert residual.dtype == torch.float32 and a.shape[0] % batch == 0
+    rows, k = a.shape[0] // batch, a.shape[1]
+    n = w.shape[0]
+    lda = _rowmajor(a, "a")
+    with _Timed("gemm", 2.0 * batch * rows * n * k):
+        _dod.call("dod_gemm_bf16", _stream(a), a=a, w=w, m=rows, n=n, k=k, lda=lda, ldw=_rowmajor(w, "w"), bias=bias,
+                  residual=residual, ldr=_rowmajor(residual, "residual"), out=out, ldo=_rowmajor(out, "out"),
+                  out_dtype=_DT[out.dtype], batch=batch, batch_stride_a=rows * lda, batch_stride_w=0,
+                  batch_stride_out=out_batch_stride)
+    return out
+
+
 def gemm_batched(a, w, out, *, bias=None, act=ACT_NONE, a_trans=False, w_trans=False):
     """out[..] = act(a[..] @ w[..].T + bias) over one or two leading batch dims:
     a [B, M, K] / [B, H, M, K], w [B, N, K] / [B, H, N, K], out [B, M, N] / [B, H, M, N]; strided views

@@ -86,7 +86,11 @@ typedef struct {
   int32_t patch_rows;
   /* batched problems (attention backward / training attention): batch > 1 runs `batch`
    * independent GEMMs whose A / W / out start batch_stride_* ELEMENTS apart (multiples of 8).
-   * batch <= 1 (or 0) is the plain 2-D problem.  No residual / a2 / patch_rows when batched.  */
+   * batch <= 1 (or 0) is the plain 2-D problem.  No residual / a2 / patch_rows when batched -- except
+   * batch_stride_w == 0: ONE W and (optionally) one fp32 residual [M, N] shared by every batch entry
+   * (m >= 512, n >= 256, fp32 output with a residual).  The patch embedding runs this way, one GEMM per
+   * image, so that an image's token rows are a TMA box (out starts at the image's first patch row,
+   * batch_stride_out = tokens per image * D, the residual is the position embedding).               */
   int64_t batch, batch_stride_a, batch_stride_w, batch_stride_out;
   /* second (inner) batch level, e.g. attention heads inside an image: batch_inner > 1 runs
    * batch * batch_inner problems; problem (bo, bi) starts at bo * batch_stride_* + bi * inner_stride_*.

@@ -120,6 +120,24 @@ def test_gemm_swiglu(ops, m):
     assert _rel(out, ref) < 1e-2
 
 
+@pytest.mark.parametrize("batch,rows,n,k", [(3, 600, 384, 592), (5, 1369, 768, 592), (2, 513, 1024, 72)])
+def test_gemm_per_image_shared_weight_and_residual(ops, batch, rows, n, k):
+    """One launch, one GEMM per image, W and the fp32 residual shared (the patch embedding): image i's rows land
+    `tokens` rows apart behind a row the GEMM must not touch (the CLS row)."""
+    g = _gen(batch * rows + n)
+    a = _randn((batch * rows, k), g).bfloat16()
+    w = _randn((n, k), g, 1 / math.sqrt(k)).bfloat16()
+    bias = _randn((n,), g)
+    res = _randn((rows + 1, n), g)
+    tokens = rows + 1
+    out = torch.full((batch * tokens, n), 7.0, device="cuda")
+    ops.gemm_per_image(a, w, bias, res[1:], out[1:], batch, tokens * n)
+    ref = (a.float() @ w.float().t() + bias).view(batch, rows, n) + res[1:]
+    got = out.view(batch, tokens, n)
+    assert torch.equal(got[:, 0], torch.full((batch, n), 7.0, device="cuda"))   # row 0 of every image untouched
+    assert _rel(got[:, 1:], ref) < 2e-5
+
+
 def test_gemm_patch_rows(ops):
     """Patch-embedding row map: GEMM row m -> token row m + m/P + 1, residual row 1 + m%P."""
     b, p, k, d = 3, 16, 592, 384
