@@ -200,9 +200,15 @@ def f32c(t):
     return t.detach().float().contiguous()
 
 
+def pair_kernel_enabled():
+    """DOD_GEMM_2CTA=0 (read by libdod as well) forces the single-CTA GEMM kernel; the LayerNorm fold and the
+    per-image patch GEMM need the CTA-pair kernel's epilogues and are switched off with it."""
+    return os.environ.get("DOD_GEMM_2CTA", "1") != "0"
+
+
 def ln_fold_enabled():
     """DOD_LN_FOLD=0 keeps every LayerNorm a standalone kernel (A/B measurements)."""
-    return os.environ.get("DOD_LN_FOLD", "1") != "0"
+    return os.environ.get("DOD_LN_FOLD", "1") != "0" and pair_kernel_enabled()
 
 
 # ---------------------------------------------------------------------------
@@ -302,7 +308,7 @@ def backbone_forward(pack: BackbonePack, pixel_values, final_norm=True):
         # fp32 mode: im2col once more in full precision (bf16 patches would cost 3 digits)
         patches = _patchify_f32(px, gh, gw)
         pack.patch(patches, residual=pos, out=x, patch_rows=p)
-    elif p >= 512 and b > 1:
+    elif p >= 512 and b > 1 and pair_kernel_enabled():
         # one GEMM per image inside ONE launch (W and the position embedding shared): an image's patch rows
         # x[i*N + 1 : (i+1)*N] are a TMA box, so the CTA-pair kernel with its TMA epilogue applies
         ops.gemm_per_image(patches, pack.patch.w, pack.patch.bias, pos[1:], x[1:], b, n * d)
