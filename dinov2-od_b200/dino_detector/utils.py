@@ -5,6 +5,11 @@ state_dict keys match; they are parameter containers -- the detector's forward r
 their tensors and runs libdod kernels, it does not call these modules' `forward`.
 The box helpers are thin torch expressions kept for API compatibility (the matcher and
 criterion hot paths use the fused kernels instead).
+
+Names of the reference's utils.py that are NOT on the hot path -- `compute_coco_metrics`,
+`setup_logger`, `setup_tensorboard`, `log_metrics`, `log_images` (reference utils.py:243-384, imported by
+train.py:22-25) -- are not re-implemented: module `__getattr__` forwards them to the reference's own
+`utils.py` from the overlaid checkout (DOD_REFERENCE_DIR, see the package docstring).
 """
 from __future__ import annotations
 
@@ -117,3 +122,43 @@ def evaluate_coco(model, dataloader, device, output_file=None):
         with open(output_file, "w") as f:
             json.dump(results, f)
     return results
+
+
+# ---------------------------------------------------------------------------
+# everything else: the reference's own utils.py (logging / TensorBoard / pycocotools glue)
+# ---------------------------------------------------------------------------
+_REFERENCE_UTILS = None
+
+
+def _reference_utils():
+    """The reference checkout's utils.py, executed once as `dino_detector._reference_utils`."""
+    global _REFERENCE_UTILS
+    if _REFERENCE_UTILS is None:
+        import importlib.util
+        import os
+        import sys
+        from . import reference_package_dir
+        ref = reference_package_dir()
+        if ref is None:
+            raise ImportError("this name lives in the reference's dino_detector/utils.py: set DOD_REFERENCE_DIR to a "
+                              "checkout of mudit1729/dinov2-od (the directory that contains dino_detector/)")
+        name = __package__ + "._reference_utils"
+        spec = importlib.util.spec_from_file_location(name, os.path.join(ref, "utils.py"))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        try:
+            spec.loader.exec_module(mod)
+        except BaseException:
+            sys.modules.pop(name, None)
+            raise
+        _REFERENCE_UTILS = mod
+    return _REFERENCE_UTILS
+
+
+def __getattr__(name):
+    if name.startswith("__"):
+        raise AttributeError(name)
+    try:
+        return getattr(_reference_utils(), name)
+    except ImportError as e:
+        raise AttributeError(f"module {__name__!r} has no attribute {name!r} ({e})") from None
