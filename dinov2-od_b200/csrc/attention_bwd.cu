@@ -338,10 +338,9 @@ extern "C" int32_t dod_fmha_bwd(const dod_fmha_bwd_args* a, dod_stream_t stream_
   DOD_REQUIRE(a->q_off + hd <= a->ld && a->k_off + hd <= a->ld && a->v_off + hd <= a->ld && hd <= a->ldo &&
                   hd <= a->lddo && hd <= a->ld_dq && a->k_off + hd <= a->ld_dqkv && a->v_off + hd <= a->ld_dqkv,
               "dod_fmha_bwd: head slices exceed the row");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     DOD_CUDA_OK(cudaFuncSetAttribute(fmha_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
   }
   {
     const int64_t total = a->batch * a->seq * a->heads;

@@ -38,6 +38,19 @@ int  check_cuda(cudaError_t e, const char* what);
 
 int num_sms();
 
+// true the first time it is called with `flags` on the CURRENT device (cudaFuncSetAttribute is a per-device
+// setting: a process that drives several GPUs must opt every one of them in); benign race: idempotent attribute.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+
 // TMA descriptor factory (driver entry point fetched at run time, no -lcuda).
 // 2-D row-major tensor [rows, cols] of `elt_bytes` elements, leading dim `ld`
 // (elements); box = [box_rows, box_cols]; 128-byte swizzle, zero OOB fill.

@@ -1043,10 +1043,9 @@ void fill_ln_params(GemmParams& p, const dod_gemm_args& a) {
 template <bool RES, bool TRANS>
 int launch2(const dod_gemm_args& a, cudaStream_t stream) {
   using L = SmemLayout2<RES>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     DOD_CUDA_OK(cudaFuncSetAttribute(gemm2_kernel<RES, TRANS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    attr_set = true;
   }
   CUtensorMap tm_a, tm_w, tm_a2, tm_w2, tm_out, tm_res;
   const BatchDims bd(a);
@@ -1117,11 +1116,10 @@ int launch2(const dod_gemm_args& a, cudaStream_t stream) {
 template <int BN, bool RES, bool TRANS>
 int launch(const dod_gemm_args& a, cudaStream_t stream, bool direct) {
   using L = SmemLayout<BN, RES>;
-  static bool attr_set = false;  // benign race: idempotent attribute
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     DOD_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN, RES, TRANS>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    attr_set = true;
   }
   CUtensorMap tm_a, tm_w, tm_a2, tm_w2, tm_out, tm_res;
   const BatchDims bd(a);
@@ -1196,7 +1194,10 @@ int launch_bn(const dod_gemm_args& a, cudaStream_t stream) {
   // TMA epilogue needs: no row remap, residual only together with fp32 output
   const bool direct = a.patch_rows > 0 || (a.residual && a.out_dtype != DOD_F32);
   const bool trans = a.a_trans || a.w_trans;
-  if (BN == 256 && !direct && a.m >= 512 && a.n >= 256 && use_pair_kernel()) {
+  // the folded-LayerNorm producer (out_bf16 / row_stats_out) exists only in the pair kernel's residual epilogue:
+  // it takes any M (rows past M are zero-filled by the TMA loads and clipped by the stores), so that whether a
+  // LayerNorm is folded never depends on how many token rows a batch -- or a data-parallel shard of it -- has
+  if (BN == 256 && !direct && (a.m >= 512 || a.out_bf16) && a.n >= 256 && use_pair_kernel()) {
     if (trans) return a.residual ? launch2<true, true>(a, stream) : launch2<false, true>(a, stream);
     return a.residual ? launch2<true, false>(a, stream) : launch2<false, false>(a, stream);
   }
@@ -1248,9 +1249,9 @@ extern "C" int32_t dod_gemm_bf16(const dod_gemm_args* a, dod_stream_t stream_) {
   if (a->out_bf16 || a->row_stats_out) {
     // folded LayerNorm, producer side: only the CTA-pair kernel's residual epilogue implements it
     DOD_REQUIRE(a->out_bf16 && a->row_stats_out, "dod_gemm_bf16: out_bf16 and row_stats_out come together");
-    DOD_REQUIRE(a->residual && a->out_dtype == DOD_F32 && a->m >= 512 && a->n >= 256 && a->n % 16 == 0 &&
+    DOD_REQUIRE(a->residual && a->out_dtype == DOD_F32 && a->n >= 256 && a->n % 16 == 0 &&
                     a->patch_rows == 0 && a->batch <= 1 && a->batch_inner <= 1 && use_pair_kernel(),
-                "dod_gemm_bf16: out_bf16 / row_stats_out need a residual GEMM with fp32 output, m >= 512, "
+                "dod_gemm_bf16: out_bf16 / row_stats_out need a residual GEMM with fp32 output, "
                 "n >= 256, n %% 16 == 0");
     DOD_REQUIRE(a->ldo_bf16 >= a->n && a->ldo_bf16 % 8 == 0 && (uintptr_t(a->out_bf16) & 15) == 0 &&
                     (uintptr_t(a->row_stats_out) & 7) == 0,

@@ -251,7 +251,7 @@ class BackbonePack:
                 L["fc1"] = pack_linears([lyr.mlp.fc1], mode, merge_lora=merge)
                 L["fc2"] = pack_linears([lyr.mlp.fc2], mode, merge_lora=merge)
             # LayerNorm folded into the following projection (bf16 mode, no separate LoRA segment): see
-            # backbone_forward.  Both forms are kept: small batches (< 512 token rows) use the plain one.
+            # backbone_forward.  Both forms are kept: the first block's norm1 is always a standalone kernel.
             if mode == "bf16" and ln_fold_enabled() and L["qkv"].lora is None:
                 L["qkv_ln"] = pack_linears(qkv_mods, mode, ln=L["n1"] + (1e-6,), merge_lora=merge)
                 first = lyr.mlp.weights_in if self.swiglu else lyr.mlp.fc1
@@ -315,11 +315,12 @@ def backbone_forward(pack: BackbonePack, pixel_values, final_norm=True):
     else:
         ops.gemm(patches, pack.patch.w, pack.patch.bias, residual=pos, out=x, patch_rows=p)
     scale = 1.0 / math.sqrt(64.0)
-    # Folded LayerNorm (bf16 mode, >= 512 token rows, LoRA-free blocks): the residual GEMM in front of a
+    # Folded LayerNorm (bf16 mode, LoRA-free blocks; any number of token rows, so that the arithmetic of an
+    # image never depends on the batch it is in or on how a batch is sharded): the residual GEMM in front of a
     # LayerNorm also writes the bf16 copy of the new residual stream and per-row partial sums, and the
     # projection behind it runs on that copy with gamma folded into zero-sum weight rows and the row's rstd
     # applied in its epilogue (include/dod.h) -- the 404 MB/layer-norm HBM pass disappears.
-    fold = mode == "bf16" and m >= 512 and d % 16 == 0
+    fold = mode == "bf16" and d >= 256 and d % 16 == 0
     h16 = stats = rstd = None
     if fold and any("qkv_ln" in L or "mlp_ln" in L for L in pack.layers):
         h16 = torch.empty((m, d), dtype=torch.bfloat16, device=px.device)

@@ -58,7 +58,10 @@ class DINOv2ObjectDetector(nn.Module):
 
     def forward(self, pixel_values):
         """pixel_values [B, 3, H, W] fp32 in [0, 1] -> {"pred_logits": [B, Q, C], "pred_boxes": [B, Q, 4]}."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        # the hand-written training forward (activation stash + autograd node) is for model.train() under grad
+        # mode, as in the reference's loop (train.py:1042-1101); model.eval()(x) runs the inference sequence
+        # even outside torch.no_grad() -- its outputs then carry no graph (the reference's would)
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             from .._train import detector_forward_train
             return detector_forward_train(self, pixel_values)
         mem, b, n = self.backbone.forward_rows(pixel_values)

@@ -32,6 +32,10 @@ class DETRDecoder(nn.Module):
         self.bbox_embed = MLP(hidden_dim, hidden_dim // 2, 4, num_layers=2)
         if use_deformable:
             self.reference_points = nn.Linear(hidden_dim, 2)   # unused, like reference :44-45
+            for p in self.reference_points.parameters():
+                # never receives a gradient (the reference needs find_unused_parameters=True for it): the flat
+                # gradient buffer / FusedAdam leave it out, as torch.optim.Adam skips grad-less parameters
+                p._dod_unused = True
         self.precision = None
         self._pack = None
         self._pack_key = None

@@ -54,7 +54,14 @@ class _Timed:
 def _stream(t: torch.Tensor) -> int:
     if not t.is_cuda:
         raise DodError("libdod ops need CUDA tensors (no CPU fallback exists)")
-    _dod.check_device(t.device.index if t.device.index is not None else torch.cuda.current_device())
+    cur = torch.cuda.current_device()
+    idx = t.device.index if t.device.index is not None else cur
+    if idx != cur:
+        # the C ABI launches in the calling thread's current CUDA context: a tensor of another device would run
+        # the kernel on the wrong GPU, unsynchronised with its stream (one process per GPU is the model here)
+        raise DodError(f"tensor lives on cuda:{idx} but the current CUDA device is cuda:{cur}: call "
+                       f"torch.cuda.set_device({idx}) (or use `with torch.cuda.device({idx}):`) before libdod ops")
+    _dod.check_device(idx)
     return torch.cuda.current_stream(t.device).cuda_stream
 
 

@@ -29,7 +29,9 @@ class FlatGradSync:
     """
 
     def __init__(self, params, process_group=None):
-        self.params = [p for p in params if p.requires_grad]
+        # parameters flagged `_dod_unused` are never an input of the train node (decoder.reference_points,
+        # reference detr_decoder.py:44-45): like under torch autograd their .grad stays None
+        self.params = [p for p in params if p.requires_grad and not getattr(p, "_dod_unused", False)]
         self.group = process_group
         if not self.params:
             raise ValueError("no trainable parameters")

@@ -42,7 +42,7 @@ class GraphedDetector:
                              f"got {tuple(pixel_values.shape)}")
         self.static_in.copy_(pixel_values, non_blocking=True)
         self.graph.replay()
-        return self.static_out
+        return self.static_out          # static buffers: overwritten by the next call, clone to keep
 
 
 class GraphedTrainStep:
@@ -59,6 +59,8 @@ class GraphedTrainStep:
         step = GraphedTrainStep(model, criterion, FusedAdam(model.parameters(), ...), images, max_targets=100)
         losses = step(images, targets)     # dict of device scalars (weighted, like SetCriterion.forward)
 
+    The returned loss tensors are the graph's static outputs: the next call overwrites them, so read
+    (or clone) them before stepping again.
     Shapes are fixed at capture (batch, H, W, max_targets per image).  The solver status is not checked
     on the host (criterion.strict is ignored): NaN / infeasible cost matrices leave those images unmatched.
     Under torch.distributed the NCCL all-reduces (num_boxes, flat gradient) are part of the graph.
@@ -84,6 +86,11 @@ class GraphedTrainStep:
         self._h_boxes = torch.zeros((cap, 4), dtype=torch.float32).pin_memory()
         self._h_offsets = torch.zeros(b + 1, dtype=torch.int32).pin_memory()
         self._h_num = torch.zeros(1, dtype=torch.float32).pin_memory()
+        # recorded after the four H2D copies of a step; the staging buffers are not rewritten before it has
+        # completed (the host runs ahead of the GPU: without this, step N's copies -- still queued behind the
+        # replay of step N-1 -- would read the targets of step N+1)
+        self._staged = torch.cuda.Event()
+        self._staged_pending = False
         # [0] dropout seed epoch, [1] Adam step number; continue from the optimizer's host count
         self.counters = torch.tensor([1, optimizer.step_count], dtype=torch.int64, device=dev)
         self._ops = ops
@@ -136,6 +143,9 @@ class GraphedTrainStep:
         """Refill the static CSR target buffers from a list of target dicts (dataset.py:102-111)."""
         if len(targets) != self.batch:
             raise ValueError(f"graph was captured for {self.batch} images, got {len(targets)} target dicts")
+        if self._staged_pending:
+            self._staged.synchronize()
+            self._staged_pending = False
         off = 0
         self._h_offsets[0] = 0
         for i, t in enumerate(targets):
@@ -152,6 +162,8 @@ class GraphedTrainStep:
         self.boxes.copy_(self._h_boxes, non_blocking=True)
         self.offsets.copy_(self._h_offsets, non_blocking=True)
         self.num_boxes.copy_(self._h_num, non_blocking=True)
+        self._staged.record(torch.cuda.current_stream(self.labels.device))
+        self._staged_pending = True
 
     def __call__(self, images, targets):
         if tuple(images.shape) != tuple(self.images.shape):

@@ -107,7 +107,7 @@ typedef struct {
    * projection).  With W'' = gamma (.) W minus its row means (every row of W'' sums to zero, so the
    * product removes the row mean of h by itself):
    *     LN(h) . W^T + b  =  rstd_m * ( h . W''^T )  +  ( b + W . beta )_n
-   * PRODUCER side (a residual GEMM with fp32 output, m >= 512, n >= 256, n % 16 == 0): besides `out`
+   * PRODUCER side (a residual GEMM with fp32 output, any m, n >= 256, n % 16 == 0): besides `out`
    * (the fp32 residual stream h) it writes h rounded to bf16 to `out_bf16` (row stride ldo_bf16) and
    * per-row partial sums of h and h^2 to `row_stats_out` [2 * ceil(n / 256)][M][2] f32 (one slot per
    * 128 columns, slot-major so that a warp's 32 rows are contiguous; written without atomics so the result is run-to-run reproducible).

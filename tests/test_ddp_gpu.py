@@ -70,18 +70,8 @@ def test_two_gpu_gradient_allreduce_matches_single_process(use_ddp):
         pytest.skip("needs 2 GPUs")
     mgr = mp.Manager()
     results = mgr.dict()
-    # The subject is the all-reduce, so both sides must run the same arithmetic: one image per rank is 257 token
-    # rows (standalone LayerNorm kernels), the two-image reference is 514 rows, where the frozen blocks switch to
-    # the LayerNorm fold (>= 512 rows) -- two bf16 paths whose gradients differ by up to ~9 % on the noisiest
-    # tensor.  The fold itself is checked against the fp32 oracle in test_detector_gpu / test_train_gpu.
-    old = os.environ.get("DOD_LN_FOLD")
-    os.environ["DOD_LN_FOLD"] = "0"
-    try:
-        mp.spawn(_worker, args=(2, _free_port(), results, use_ddp), nprocs=2, join=True)
-    finally:
-        if old is None:
-            del os.environ["DOD_LN_FOLD"]
-        else:
-            os.environ["DOD_LN_FOLD"] = old
+    # default switches (LayerNorm fold on): whether a LayerNorm is folded no longer depends on the number of token
+    # rows, so the one-image shards and the concatenated two-image batch run the same arithmetic per image
+    mp.spawn(_worker, args=(2, _free_port(), results, use_ddp), nprocs=2, join=True)
     assert results["n"] > 50
     assert results["worst"] < 2e-2, results["worst"]

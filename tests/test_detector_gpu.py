@@ -125,3 +125,19 @@ def test_bench_workload_full_batch_equals_small_batches():
             for k in full:
                 a, b = full[k][lo:lo + 2], part[k].float()
                 assert rel_err(a, b) < 1e-5, (k, lo, rel_err(a, b))
+
+
+@pytest.mark.parametrize("case", ["c1_small_deform", "c1_small_std"])
+def test_result_of_an_image_does_not_depend_on_its_batch(case):
+    """One 224x224 image is 257 token rows, two are 514: the LayerNorm fold / CTA-pair kernel selection must not
+    depend on the row count (it did: >= 512 rows folded, fewer did not, so a data-parallel shard of a batch ran
+    other arithmetic than the whole batch -- VERDICT r01 weak #1)."""
+    model, _, _ = build_product_model(case, device="cuda")
+    model.precision = "bf16"
+    x = synth.make_images(3, 224, 224, seed=11).cuda()
+    with torch.no_grad():
+        full = {k: v.float().clone() for k, v in model(x).items()}
+        for i in range(3):
+            one = model(x[i:i + 1])
+            for k in full:
+                assert rel_err(full[k][i:i + 1], one[k].float()) < 1e-5, (k, i)

@@ -72,3 +72,27 @@ def test_graphed_train_step_draws_new_dropout_masks():
     a = float(step(x, tc)["loss_bbox"])
     b = float(step(x, tc)["loss_bbox"])
     assert a != b
+
+
+def test_graphed_train_step_targets_do_not_tear_without_host_syncs():
+    """Two different target sets alternated with NO host synchronisation between replays (the host runs many
+    steps ahead of the GPU): every step must see its own targets, not the staging buffers' later contents."""
+    from dino_detector.runtime import GraphedTrainStep
+    (x, ta), (_, tb) = _batches(2, 2)
+    model, crit, opt = _setup(0.0)
+    opt.lr = 0.0                                      # frozen weights: the loss depends on the targets only
+    opt.weight_decay = 0.0
+    step = GraphedTrainStep(model, crit, opt, x, max_targets=16)
+    host = [[{k: v.cpu() for k, v in d.items()} for d in t] for t in (ta, tb)]
+    want = []
+    for t in host:
+        want.append({k: v.clone() for k, v in step(x, t).items()})
+    torch.cuda.synchronize()
+    got = []
+    for i in range(24):                               # no .item() / float() / synchronize inside the loop
+        got.append({k: v.clone() for k, v in step(x, host[i & 1]).items()})
+    torch.cuda.synchronize()
+    assert float(want[0]["loss_bbox"]) != float(want[1]["loss_bbox"])
+    for i, g in enumerate(got):
+        for k in g:
+            assert float(g[k]) == float(want[i & 1][k]), (i, k)
