@@ -55,6 +55,9 @@ class SetCriterion(nn.Module):
         # strict: check the solver status on the host (one tiny D2H sync) and raise ValueError like
         # scipy does for NaN / infeasible costs; False keeps the whole step free of host syncs.
         self.strict = True
+        # losses.py:228-230 all-reduces num_boxes whenever torch.distributed is initialised; False keeps this
+        # rank's count (a single-process evaluation of a whole batch inside a multi-rank job, e.g. a parity check)
+        self.sync_num_boxes = True
 
     def forward(self, outputs, targets):
         dev = outputs["pred_logits"].device
@@ -74,7 +77,7 @@ class SetCriterion(nn.Module):
         if self.strict and bool((status != 0).any()):
             raise ValueError("matrix contains invalid numeric entries")
         # losses.py:228-230: all-reduced with SUM (no / world), clamp(min=1)
-        if dist.is_available() and dist.is_initialized():
+        if self.sync_num_boxes and dist.is_available() and dist.is_initialized():
             num_boxes = num_boxes.clone()
             dist.all_reduce(num_boxes)
         num_boxes = torch.clamp(num_boxes, min=1)

@@ -1,5 +1,6 @@
-"""bench.py contract checks that need no GPU: the reference arm (the CPU oracle port timed on the host cores)
-prints exactly ONE JSON line on stdout with the keys the driver reads."""
+"""bench.py contract checks that need no GPU: the reference arm (the UNMODIFIED reference from baseline/_ref timed on
+the host cores) prints exactly ONE JSON line on stdout with the keys the driver reads, and its `config` is the repo
+arm's, byte for byte."""
 import json
 import os
 import subprocess
@@ -18,7 +19,10 @@ def test_reference_arm_prints_one_json_line():
     j = json.loads(lines[0])
     assert j["impl"] == "reference" and j["higher_is_better"] is True and j["n_gpus"] == 1
     assert j["unit"] == "images/s" and j["value"] > 0 and j["steps"] == 1
-    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
+    assert j["cpu_baseline"]["kind"] == "reference" and j["cpu_baseline"]["cores"] >= 1
+    sys.path.insert(0, ROOT)
+    import bench
+    assert j["config"] == bench._config(1)              # same config object as the repo arm prints
     assert j["e2e"]["value"] == j["value"] and j["e2e"]["h2d_bytes_per_step"] == 0
     assert "workload" in j["config"] and j["vs_baseline"] is None
 
