@@ -355,7 +355,7 @@ class Ctx:
 
     def rate_record(self, images_per_step_global, ms_total, steps, gflops_per_image, **extra):
         ms = ms_total / steps
-        tf = gflops_per_image * images_per_step_global / self.world / ms / 1e3       # per GPU
+        tf = gflops_per_image * images_per_step_global / self.world / ms             # GF / ms = TFLOP/s, per GPU
         rec = {"value": images_per_step_global / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps,
                "n_gpus": self.world, "images_per_gpu_per_step": images_per_step_global // self.world,
                "gflops_per_image": round(gflops_per_image, 2), "model_tflops_per_gpu": tf,
@@ -626,7 +626,7 @@ def run_ours(args):
     gemm_tflops = gf / (gt * 1e-3) / 1e12
     fmha_tflops = ff / (ft * 1e-3) / 1e12
     fwd = forward_gflops("base")
-    step_tflops = fwd["total"] * BATCH / (head["ms_local"] / steps) / 1e3
+    step_tflops = fwd["total"] * BATCH / (head["ms_local"] / steps)            # GF / ms = TFLOP/s
     roof = {"kernel": "dod::gemm2_kernel / gemm_kernel (tcgen05 cta_group::2, TMEM, TMA)", "bound": "tensor",
             "achieved": gemm_tflops, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": gemm_tflops / peaks["tflops"],
             "frac_of_burst": gemm_tflops / peaks["tflops_burst"], "peak_burst": peaks["tflops_burst"],

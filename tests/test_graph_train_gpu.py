@@ -92,7 +92,9 @@ def test_graphed_train_step_targets_do_not_tear_without_host_syncs():
     for i in range(24):                               # no .item() / float() / synchronize inside the loop
         got.append({k: v.clone() for k, v in step(x, host[i & 1]).items()})
     torch.cuda.synchronize()
-    assert float(want[0]["loss_bbox"]) != float(want[1]["loss_bbox"])
+    # the loss sums are fp32 atomics (last-bit run-to-run noise); a torn / next-step target set changes them by percents
+    for k in want[0]:
+        assert abs(float(want[0][k]) - float(want[1][k])) > 1e-3 * abs(float(want[0][k])), k
     for i, g in enumerate(got):
         for k in g:
-            assert float(g[k]) == float(want[i & 1][k]), (i, k)
+            assert abs(float(g[k]) - float(want[i & 1][k])) <= 1e-5 * abs(float(want[i & 1][k])), (i, k)
