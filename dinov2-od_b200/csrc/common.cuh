@@ -163,16 +163,66 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps (launch fails with an error) instead of
-// hanging the GPU.  try_wait sleeps in hardware, so the bound is generous.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// hanging the GPU.  try_wait sleeps in hardware, so the bound is generous.  The report is out of line
+// so that every wait site is four instructions, not forty (the persistent attention kernel has ~30 sites
+// and paid for the inlined printf sequences with instruction-cache misses).
+static __device__ __noinline__ void mbar_timeout(uint32_t bar_addr, uint32_t parity) {
+  printf("dod: mbarrier timeout block=(%d,%d,%d) thread=%d bar=0x%x parity=%u\n", blockIdx.x, blockIdx.y,
+         blockIdx.z, threadIdx.x, bar_addr, parity);
+  __trap();
+}
+__device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar_addr), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parity) {
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > 20000000u) {
-      printf("dod: mbarrier timeout block=(%d,%d,%d) thread=%d bar=%p parity=%u\n", blockIdx.x,
-             blockIdx.y, blockIdx.z, threadIdx.x, (void*)bar, parity);
-      __trap();
-    }
+  while (!mbar_try_wait_addr(bar_addr, parity)) {
+    if (++spins > 20000000u) mbar_timeout(bar_addr, parity);
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_addr(smem_u32(bar), parity); }
+__device__ __forceinline__ bool mbar_test_wait_addr(uint32_t bar_addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar_addr), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// one elected lane of the (converged) warp arrives: predicated instruction, no divergent branch
+__device__ __forceinline__ void mbar_arrive_elect_addr(uint32_t bar_addr) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t"
+      "}" ::"r"(bar_addr)
+      : "memory");
+}
+// shared-memory scalar access by 32-bit shared address (a generic pointer costs a cvta sequence and is
+// tracked on the long scoreboard like a global access)
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
 }
 
 // ---- TMA ----
