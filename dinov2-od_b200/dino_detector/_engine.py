@@ -421,6 +421,15 @@ class DecoderPack:
                 # every entry is the same module, pack it once.
                 self.layers = [L] * len(layers)
                 break
+        self.ca_kv_all = None
+        if not self.deformable:
+            # the standard decoder's layers all project the SAME memory (reference detr_decoder.py:62-69 passes
+            # it to every nn.TransformerDecoderLayer): one GEMM [B*N, h] x [h, 2h*L] reads it once instead of L
+            # times; layer i takes columns [2h*i, 2h*(i+1)) of the result
+            hd = self.h
+            w = torch.cat([l.multihead_attn.in_proj_weight.detach()[hd:] for l in layers], dim=0)
+            b = torch.cat([l.multihead_attn.in_proj_bias.detach()[hd:] for l in layers], dim=0)
+            self.ca_kv_all = pack_raw(w, b, mode)
         self.cls = pack_linears([dec.class_embed], mode)
         self.box0 = pack_linears([dec.bbox_embed.mlp[0]], mode)
         self.box1 = pack_linears([dec.bbox_embed.mlp[2]], mode)
@@ -434,6 +443,28 @@ def _post_norm(x_f32, ln, adt):
         return y, y
     y32, y16 = ops.layernorm(x_f32, *ln, 1e-5, out_dtype=torch.float32, also_other=True)
     return y32, y16
+
+
+def _heads_view(x2, b, l, heads, dh):
+    """[B*L, >= H*dh] rows (unit inner stride) -> [B, H, L, dh] strided view, no copy."""
+    ld = x2.stride(0)
+    return x2.as_strided((b, heads, l, dh), (l * ld, dh, ld, 1), x2.storage_offset())
+
+
+def cross_attention_tc(q2, k2, v2, b, lq, lk, heads, dh, scale):
+    """Few-query attention over a long memory on the tensor cores (bf16 mode): S = Q K^T and ctx = P V run as
+    ONE batched tcgen05 GEMM each over every (image, head) through 4-D TMA maps, the row softmax in between is
+    one pass over the fp32 scores (reference nn.MultiheadAttention inside nn.TransformerDecoderLayer,
+    detr_decoder.py:29-35).  q2 [B*Lq, H*dh], k2 / v2 [B*Lk, >= H*dh] row views -> ctx bf16 [B*Lq, H*dh]."""
+    lkp = _pad8(lk)
+    dev = q2.device
+    ctx = torch.empty((b * lq, heads * dh), dtype=torch.bfloat16, device=dev)
+    s_full = torch.empty((b, heads, lq, lkp), dtype=torch.float32, device=dev)
+    ops.gemm_batched(_heads_view(q2, b, lq, heads, dh), _heads_view(k2, b, lk, heads, dh), s_full[..., :lk])
+    p = ops.softmax_rows(s_full.view(-1, lkp), lk, scale, ldp=lkp)
+    ops.gemm_batched(p.view(b, heads, lq, lkp)[..., :lk], _heads_view(v2, b, lk, heads, dh),
+                     _heads_view(ctx, b, lq, heads, dh), w_trans=True)
+    return ctx
 
 
 def decoder_forward(pack: DecoderPack, memory, b, n):
@@ -453,7 +484,10 @@ def decoder_forward(pack: DecoderPack, memory, b, n):
         if gh * gw != n:
             # reference deformable_attention.py:76-82
             raise ValueError(f"Cannot reshape input of size {n} into a square feature map")
-    for L in pack.layers:
+    kv_all = None
+    if not pack.deformable and len(pack.layers) > 1 and os.environ.get("DOD_KV_BATCHED", "1") != "0":
+        kv_all = pack.ca_kv_all(memory)                        # [B*N, 2h * L]: K/V of every layer in one GEMM
+    for li, L in enumerate(pack.layers):
         # --- self attention (nn.MultiheadAttention, deformable_attention.py:232-235) ---
         qkv = L["sa_in"](tgt)
         ctx = ops.mha_small(qkv[:, :hd], qkv[:, hd:2 * hd], qkv[:, 2 * hd:], b, q, q, heads, dh, scale)
@@ -470,8 +504,11 @@ def decoder_forward(pack: DecoderPack, memory, b, n):
             x = L["out"](samp, residual=tgt32, out_dtype=torch.float32)
         else:
             cq = L["ca_q"](tgt)
-            kv = L["ca_kv"](memory)                            # [B*N, 2h]
-            ctx = ops.mha_small(cq, kv[:, :hd], kv[:, hd:], b, q, n, heads, dh, scale)
+            kv = kv_all[:, 2 * hd * li:2 * hd * (li + 1)] if kv_all is not None else L["ca_kv"](memory)
+            if mode == "bf16" and n > 128 and dh % 8 == 0 and os.environ.get("DOD_CROSS_ATTN_TC", "1") != "0":
+                ctx = cross_attention_tc(cq, kv[:, :hd], kv[:, hd:], b, q, n, heads, dh, scale)
+            else:                                              # fp32 parity mode / short memories
+                ctx = ops.mha_small(cq, kv[:, :hd], kv[:, hd:], b, q, n, heads, dh, scale)
             x = L["ca_out"](ctx, residual=tgt32, out_dtype=torch.float32)
         tgt32, tgt = _post_norm(x, L["n2"], adt)
         # --- FFN ---

@@ -287,6 +287,28 @@ def test_fmha_bench_shape_full_size(ops):
         assert (out[bi, :, hi].float() - exact).abs().max().item() < 1e-2
 
 
+@pytest.mark.parametrize("b,lq,lk,h,dh", [(3, 100, 257, 4, 64), (2, 100, 1370, 8, 96), (1, 25, 1370, 8, 128),
+                                          (2, 50, 300, 6, 192), (64, 100, 1370, 8, 96)])
+def test_cross_attention_on_tensor_cores(b, lq, lk, h, dh):
+    """Standard-decoder cross-attention (few queries x long memory) as batched tcgen05 GEMMs + row softmax
+    (_engine.cross_attention_tc) vs fp32 torch on the same bf16 inputs; K and V are column slices of ONE fused
+    projection buffer like in the decoder (stride 2 * hidden * layers)."""
+    from dino_detector import _engine
+    g = _gen(lq * 3 + lk + dh)
+    d = h * dh
+    q = _randn((b * lq, d), g).bfloat16()
+    kv = _randn((b * lk, 3 * 2 * d), g).bfloat16()               # three layers' K | V side by side
+    k, v = kv[:, 2 * d:3 * d], kv[:, 3 * d:4 * d]                 # layer 1
+    out = _engine.cross_attention_tc(q, k, v, b, lq, lk, h, dh, 1 / math.sqrt(dh))
+    for bi in sorted({0, b // 2, b - 1}):
+        qf = q[bi * lq:(bi + 1) * lq].float().view(lq, h, dh).transpose(0, 1)
+        kf = k[bi * lk:(bi + 1) * lk].float().view(lk, h, dh).transpose(0, 1)
+        vf = v[bi * lk:(bi + 1) * lk].float().view(lk, h, dh).transpose(0, 1)
+        ref = (torch.softmax(qf @ kf.transpose(1, 2) / math.sqrt(dh), dim=-1) @ vf).transpose(0, 1).reshape(lq, d)
+        got = out[bi * lq:(bi + 1) * lq].float()
+        assert (got - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item()), (bi,)
+
+
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32])
 @pytest.mark.parametrize("b,lq,lk,h,dh", [(2, 50, 50, 8, 96), (3, 100, 257, 4, 64), (1, 25, 1370, 8, 96),
                                           (2, 17, 33, 4, 192), (1, 100, 100, 8, 96), (2, 128, 128, 4, 64)])
