@@ -119,17 +119,27 @@ add_layernorm_kernel(const float* __restrict__ x, const void* __restrict__ r,
 
 }  // namespace
 __global__ void ln_rstd_kernel(const float2* __restrict__ stats, float* __restrict__ rstd, int64_t rows,
-                               int slots, float inv_dim, float eps) {
+                               int slots, float inv_dim, float eps, float* __restrict__ max_ratio) {
   const int64_t row = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (row >= rows) return;
-  float s1 = 0.0f, s2 = 0.0f;
-  for (int i = 0; i < slots; ++i) {
-    const float2 v = __ldg(stats + int64_t(i) * rows + row);
-    s1 += v.x;
-    s2 += v.y;
+  float ratio = 0.0f;
+  if (row < rows) {
+    float s1 = 0.0f, s2 = 0.0f;
+    for (int i = 0; i < slots; ++i) {
+      const float2 v = __ldg(stats + int64_t(i) * rows + row);
+      s1 += v.x;
+      s2 += v.y;
+    }
+    const float mean = s1 * inv_dim;
+    const float r = rsqrtf(fmaxf(s2 * inv_dim - mean * mean, 0.0f) + eps);
+    rstd[row] = r;
+    ratio = fabsf(mean) * r;
   }
-  const float mean = s1 * inv_dim;
-  rstd[row] = rsqrtf(fmaxf(s2 * inv_dim - mean * mean, 0.0f) + eps);
+  if (max_ratio != nullptr) {
+    // non-negative floats order like their bit patterns: one integer atomicMax per warp
+    ratio = warp_max(ratio);
+    if ((threadIdx.x & 31) == 0 && ratio > 0.0f && isfinite(ratio))
+      atomicMax(reinterpret_cast<unsigned int*>(max_ratio), __float_as_uint(ratio));
+  }
 }
 
 }  // namespace dod
@@ -142,7 +152,8 @@ extern "C" int32_t dod_ln_rstd(const dod_ln_rstd_args* a, dod_stream_t stream_) 
   DOD_REQUIRE((uintptr_t(a->row_stats) & 7) == 0, "dod_ln_rstd: row_stats must be 8-byte aligned");
   if (a->rows == 0) return DOD_OK;
   ln_rstd_kernel<<<unsigned((a->rows + 255) / 256), 256, 0, stream>>>(
-      reinterpret_cast<const float2*>(a->row_stats), a->rstd, a->rows, int(a->slots), 1.0f / float(a->dim), a->eps);
+      reinterpret_cast<const float2*>(a->row_stats), a->rstd, a->rows, int(a->slots), 1.0f / float(a->dim), a->eps,
+      a->max_mean_ratio);
   int rc = check_cuda(cudaGetLastError(), "ln_rstd_kernel launch");
   if (rc == 0) count_launch();
   return rc;

@@ -167,6 +167,19 @@ class DINOv2Backbone(nn.Module):
             self._fpack_key = key
         return self._fpack
 
+    def ln_fold_max_mean_ratio(self, reset=False):
+        """Largest |row mean| / row std any folded LayerNorm of this backbone has seen so far (reading it syncs).
+        The folded form rounds the un-normalised residual stream to bf16, so its noise relative to the normalised
+        signal grows like sqrt(1 + ratio^2): well below 1 it equals the standalone kernel's; if a checkpoint
+        drives it above ~3, run with DOD_LN_FOLD=0."""
+        best = 0.0
+        for pk in (self._pack, getattr(self, "_fpack", None)):
+            if pk is not None and getattr(pk, "ln_monitor", None) is not None:
+                best = max(best, float(pk.ln_monitor.item()))
+                if reset:
+                    pk.ln_monitor.zero_()
+        return best
+
     def forward_rows(self, pixel_values):
         """-> (memory [B*N, out_dim] in the activation dtype, B, N)."""
         return _engine.backbone_forward(self._get_pack(), pixel_values)

@@ -121,14 +121,17 @@ def gemm(a, w, bias=None, *, act=ACT_NONE, scale=None, residual=None, out=None,
     return out
 
 
-def ln_rstd(row_stats, dim, eps, out=None):
-    """rstd [M] from the partial sums [slots, M, 2] a residual GEMM wrote through ln_out (folded LayerNorm)."""
+def ln_rstd(row_stats, dim, eps, out=None, max_mean_ratio=None):
+    """rstd [M] from the partial sums [slots, M, 2] a residual GEMM wrote through ln_out (folded LayerNorm).
+    max_mean_ratio: optional f32 [1] device tensor that keeps the running maximum of |mean| * rstd over all rows."""
     slots, m, _ = row_stats.shape
     assert row_stats.dtype == torch.float32 and row_stats.is_contiguous()
     if out is None:
         out = torch.empty(m, dtype=torch.float32, device=row_stats.device)
+    if max_mean_ratio is not None:
+        assert max_mean_ratio.dtype == torch.float32 and max_mean_ratio.numel() == 1
     _dod.call("dod_ln_rstd", _stream(row_stats), row_stats=row_stats, rstd=out, slots=slots, rows=m, dim=int(dim),
-              eps=float(eps))
+              eps=float(eps), max_mean_ratio=max_mean_ratio)
     return out
 
 

@@ -58,6 +58,10 @@ class FlatGradSync:
             if p.grad is None or p.grad.data_ptr() < self.flat.data_ptr() or \
                     p.grad.data_ptr() >= self.flat.data_ptr() + self.flat.numel() * 4:
                 raise RuntimeError("FlatGradSync: p.grad is no longer a view of the flat buffer; call attach()")
+        if average and dist.get_backend(self.group) == "nccl":
+            # NCCL averages inside the collective (no separate pass over the buffer afterwards)
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+            return self.flat
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
         if average:
             self.flat.div_(dist.get_world_size(self.group))

@@ -122,12 +122,16 @@ typedef struct {
 DOD_API int32_t dod_gemm_bf16(const dod_gemm_args* a, dod_stream_t stream);
 
 /* rstd[m] = rsqrt(var_m + eps) from the per-row partial sums a producer GEMM wrote (folded LayerNorm above;
- * nn.LayerNorm statistics of modeling_dinov2.py:354,359 in fp32).                                        */
+ * nn.LayerNorm statistics of modeling_dinov2.py:354,359 in fp32).
+ * max_mean_ratio (optional): running maximum over all rows seen of |mean_m| * rstd_m.  The folded form feeds
+ * bf16(h) instead of bf16(LN(h)) to the projection, so its rounding noise relative to the normalised signal grows
+ * with this ratio (equal at 0, ~sqrt(1 + ratio^2) x otherwise); a monitor, never read on the hot path.        */
 typedef struct {
   const float* row_stats; /* f32 [slots][rows][2]: partial sums of h and h^2 */
   float* rstd;            /* f32 [rows]                                      */
   int64_t slots, rows, dim;
   float eps;
+  float* max_mean_ratio;  /* f32 [1] (>= 0, atomically maximised) or NULL    */
 } dod_ln_rstd_args;
 DOD_API int32_t dod_ln_rstd(const dod_ln_rstd_args* a, dod_stream_t stream);
 

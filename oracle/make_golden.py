@@ -59,11 +59,20 @@ def import_reference():
 
 
 def main():
+    """`python oracle/make_golden.py [case ...]`: no arguments regenerates everything; case names regenerate only
+    those detector fixtures (the manifest entries of the others are kept)."""
     os.makedirs(GOLDEN, exist_ok=True)
     ref_models, ref_matching, ref_losses = import_reference()
     torch.set_grad_enabled(False)
+    only = set(sys.argv[1:])
     manifest = {}
+    man_path = os.path.join(GOLDEN, "manifest.json")
+    if only and os.path.exists(man_path):
+        with open(man_path) as fh:
+            manifest = json.load(fh)
     for name, case in synth.CASES.items():
+        if only and name not in only:
+            continue
         kw = synth.case_ctor(name)
         _LAYER_OVERRIDE["n"] = case.get("backbone_layers")
         model = ref_models.DINOv2ObjectDetector(**kw).eval()
@@ -88,6 +97,10 @@ def main():
                               n_keys=len(sd))
         del model, sd
 
+    if only:
+        with open(man_path, "w") as fh:
+            json.dump(manifest, fh, indent=1, sort_keys=True)
+        return
     # ---- matcher: reference HungarianMatcher (matching.py:42-122, scipy LSA) ----
     matcher = ref_matching.HungarianMatcher(cost_class=1, cost_bbox=5, cost_giou=2)
     for tag, (bs, q, max_gt) in {"q100": (16, 100, 50), "q25": (8, 25, 50), "dupes": (4, 50, 20)}.items():

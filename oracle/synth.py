@@ -177,6 +177,11 @@ CASES = {
     "giant3_swiglu": dict(ctor=dict(dino_model_name="facebook/dinov2-giant", hidden_dim=None, lora_r=2,
                                     num_queries=50, nheads=8),
                           batch=1, hw=(224, 224), backbone_layers=3),
+    # full-depth g/14 (40 SwiGLU blocks, 24 heads), default constructor otherwise (projection 1536 -> 768):
+    # the model tools / bench.py time as config 5
+    "giant40_full": dict(ctor=dict(dino_model_name="facebook/dinov2-giant"), batch=1, hw=(224, 224)),
+    # config 4's model exactly as stated: L/14, LoRA r=8, default (deformable) decoder, 518x518
+    "large_r8_deform_518": dict(ctor=dict(dino_model_name="facebook/dinov2-large", lora_r=8), batch=1, hw=(518, 518)),
 }
 
 CTOR_DEFAULTS = dict(num_classes=91, dino_model_name="facebook/dinov2-base", lora_r=2, lora_alpha=1.0,

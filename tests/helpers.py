@@ -55,3 +55,22 @@ def oracle_forward(sd, x, kw):
 def rel_err(a, b):
     a, b = a.detach().float().cpu(), b.detach().float().cpu()
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def record_margin(case, what, value, tol, **extra):
+    """Append the ACHIEVED error of a parity check next to its tolerance to a JSON-lines file
+    ($DOD_MARGINS_FILE, default gpurun_out/parity_margins.jsonl; tools/collect_margins.py turns it into
+    profiles/rNN_parity_margins.json) -- so that the distance to the bar is on record, not just pass / fail."""
+    path = os.environ.get("DOD_MARGINS_FILE", os.path.join(ROOT, "gpurun_out", "parity_margins.jsonl"))
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        with open(path, "a") as fh:
+            fh.write(json.dumps(dict(case=case, what=what, value=float(value), tol=float(tol), **extra)) + "\n")
+    except OSError:
+        pass
+
+
+def rel_err_rms(a, b):
+    """RMS of the difference over the RMS of the reference (a tighter reading of "relative" than rel_err)."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt().clamp_min(1e-30)).item()
