@@ -248,6 +248,14 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
       uint32_t sraw[2][32];
       tmem_ld_32x32(t_lane + kColS + half * 64, sraw[0]);
       tmem_ld_32x32(t_lane + kColS + half * 64 + 32, sraw[1]);
+      if (j > 0) {
+        // P of the previous tile: its tcgen05.st was issued at the end of that iteration; the completion wait
+        // and the p_full arrival sit HERE, under the latency of the score load just issued
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        mbar_arrive_elect_addr(smem_u32(p_full));
+      }
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
@@ -319,12 +327,12 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
         }
       }
       tmem_st_32x32(t_lane + kColP + half * 32, pk);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      mbar_arrive_elect_addr(smem_u32(p_full));
       TRACE(half, j, 6, 0);
     }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    mbar_arrive_elect_addr(smem_u32(p_full));  // P of the last tile
 
     // ---- epilogue: O / l -> ctx ----
     xsum[half * kTile + row] = l;
