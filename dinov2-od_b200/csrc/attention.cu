@@ -3,15 +3,19 @@
 // One CTA per (batch, head, 128-query tile).  Flash-style single pass over the
 // keys in tiles of 128:
 //     S = Q.K^T           tcgen05.mma  (SS: Q, K from 128B-swizzled smem)   -> TMEM
-//     P = exp2(S*c - m)   8 softmax warps, two threads per query row (64 key columns each,
-//                         row maximum exchanged through shared memory), S held in registers
+//     P = exp2(S*c - m)   4 softmax warps, one thread per query row (all 128 key columns of the
+//                         tile in registers: no row-maximum exchange), 168 registers per thread
 //     O += P.V            tcgen05.mma  (TS: P from TMEM as bf16, V MN-major smem)
 // O stays in TMEM for the whole pass; the running max is only advanced (and O
 // rescaled through tcgen05.ld/st) when it grows by more than 2^8, so the common
 // iteration touches O not at all.  K and V are double-buffered TMA rings fed by two
 // single-thread issue warps (Q/K loads + Q.K^T, V loads + P.V); the S_{j+1} MMA is
 // issued as soon as S_j has been pulled into registers so the tensor pipe runs under
-// the softmax.  Two CTAs are resident per SM (87 KB smem, 256 TMEM columns each).
+// the softmax.  Two CTAs are resident per SM (87 KB smem, 256 TMEM columns, 192 threads each).
+// Round 1 ran two threads per row (256 softmax threads at 96 registers, 605 us on the bench shape);
+// thread-per-row removes the shared-memory exchange and halves the warps that pay the per-tile barrier
+// round trips (warps issue in order): 567 us; second half of the row loaded under the first half's
+// maximum, P-store completion under the next score load: 563 us (cuDNN SDPA: 491 us).
 // The XU pipe (16 ex2/clk/SM) sets the floor: 1045 clk per 128x128 tile per SM measured for the bare
 // instruction mix (tools/ubench/softmax_mix.cu); this kernel runs at ~1300 clk per tile plus the
 // prologue / epilogue of each CTA.  profiles/r01_summary.md and r02_summary.md hold the measured phase
@@ -38,10 +42,10 @@ constexpr int kTileBytes = kTile * kD * 2;  // 16 KB
 constexpr int kKVStages = 2;
 constexpr uint32_t kTmemCols = 256;
 constexpr uint32_t kColS = 0, kColP = 128, kColO = 192;
-constexpr int kSoftmaxThreads = 256;  // two threads per query row (64 key columns each)
+constexpr int kSoftmaxThreads = 128;            // one thread per query row
 constexpr int kThreads = kSoftmaxThreads + 64;  // + Q.K^T issue warp + P.V issue warp
-constexpr int kXchgBytes = 2 * 2 * kTile * 4 + 2 * kTile * 4;  // max exchange (double buffered) + sums
-constexpr int kSmemBytes = kTileBytes * (1 + 2 * kKVStages) + 256 + kXchgBytes + 1024;
+constexpr int kChunks = kTile / 32;             // 32-column register chunks of a score row
+constexpr int kSmemBytes = kTileBytes * (1 + 2 * kKVStages) + 256 + 1024;
 
 // raw MUFU.EX2 (flush-to-zero): exp2f() wraps it in a denormal-range test + two multiplies per
 // element, which doubled the issue slots of the softmax loop
@@ -83,10 +87,16 @@ struct FmhaParams {
   float* lse;  // optional [B, heads, S]
 };
 
-__device__ __forceinline__ void pair_sync(int quad) {
-  // the two warps that share a TMEM lane quadrant (rows quad*32 .. +31)
-  asm volatile("bar.sync %0, 64;" ::"r"(quad + 1) : "memory");
+// compiler fence for registers filled by an asynchronous tcgen05.ld whose wait is not adjacent to it: uses placed
+// after this cannot be scheduled before the tcgen05.wait::ld that precedes it (volatile asms keep their order)
+__device__ __forceinline__ void regs_ready32(uint32_t (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 16)
+    asm volatile("" : "+r"(v[i]), "+r"(v[i + 1]), "+r"(v[i + 2]), "+r"(v[i + 3]), "+r"(v[i + 4]), "+r"(v[i + 5]),
+                      "+r"(v[i + 6]), "+r"(v[i + 7]), "+r"(v[i + 8]), "+r"(v[i + 9]), "+r"(v[i + 10]),
+                      "+r"(v[i + 11]), "+r"(v[i + 12]), "+r"(v[i + 13]), "+r"(v[i + 14]), "+r"(v[i + 15]));
 }
+
 
 __global__ void __launch_bounds__(kThreads, 2)
 fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
@@ -107,8 +117,6 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
   uint64_t* p_full = bars + 11;
   uint64_t* o_full = bars + 12;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
-  float* xmax = reinterpret_cast<float*>(bars + 32);  // [2 (tile parity)][2 (half)][128 rows]
-  float* xsum = xmax + 2 * 2 * kTile;                 // [2 (half)][128 rows]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -222,32 +230,31 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
       }
     }
   } else {
-    // ---------------- softmax warps: two threads per query row ----------------
-    const int quad = warp & 3;   // TMEM lane quadrant
-    const int half = warp >> 2;  // key columns [half*64, +64) of every tile; O columns [half*32, +32)
+    // ---------------- softmax warps: one thread per query row ----------------
+    const int quad = warp & 3;         // TMEM lane quadrant
     const int row = quad * 32 + lane;  // row within the tile == TMEM lane
     const uint32_t t_lane = tmem + (uint32_t(quad * 32) << 16);
     float m_used = -INFINITY;  // in log2 units (already scaled)
-    float l = 0.0f;            // partial row sum over this thread's columns
-    const uint32_t xmax_addr = smem_u32(xmax);
+    float l = 0.0f;            // row sum
 
     // s_ready / o_ready: the barrier was already seen complete by an early non-blocking test issued
     // in the middle of the previous / this exp2 phase (the MUFU pipe is the limiter there, the ~100-cycle
     // barrier instruction hides under it)
     bool s_ready = false;
     for (int j = 0; j < n_kv; ++j) {
-      TRACE(half, j, 0, 0);
+      TRACE(0, j, 0, 0);
       if (!s_ready) mbar_wait(s_full, j & 1);
       tc_fence_after();
       bool o_ready = j == 0;
       s_ready = false;
-      TRACE(half, j, 1, 0);
-      const int valid = p.seq - j * kTile - half * 64;  // keys valid in this thread's 64 columns
-      // S is read from TMEM once and held in 64 registers (two-pass and polynomial-exp2 variants were
-      // measured slower: profiles/r01_summary.md)
-      uint32_t sraw[2][32];
-      tmem_ld_32x32(t_lane + kColS + half * 64, sraw[0]);
-      tmem_ld_32x32(t_lane + kColS + half * 64 + 32, sraw[1]);
+      TRACE(0, j, 1, 0);
+      const int valid = p.seq - j * kTile;  // keys valid in this tile
+      // S is read from TMEM once and held in 128 registers (two-pass and polynomial-exp2 variants were
+      // measured slower: profiles/r01_summary.md, r02_summary.md), in two groups of two 32-column chunks
+      uint32_t sraw[kChunks][32];
+      constexpr int kFirst = kChunks / 2;
+#pragma unroll
+      for (int c = 0; c < kFirst; ++c) tmem_ld_32x32(t_lane + kColS + c * 32, sraw[c]);
       if (j > 0) {
         // P of the previous tile: its tcgen05.st was issued at the end of that iteration; the completion wait
         // and the p_full arrival sit HERE, under the latency of the score load just issued
@@ -257,33 +264,37 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
         mbar_arrive_elect_addr(smem_u32(p_full));
       }
       tmem_ld_wait();
+      // the second half of the row is loaded while the maximum of the first half is reduced
+#pragma unroll
+      for (int c = kFirst; c < kChunks; ++c) tmem_ld_32x32(t_lane + kColS + c * 32, sraw[c]);
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+      auto mask_max = [&](int c0, int c1) {
+        if (valid < kTile) {
+          // tail tile only (1370 = 10*128 + 90): keys beyond the sequence get -inf
+#pragma unroll
+          for (int c = c0; c < c1; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= valid) sraw[c][i] = 0xff800000u;
+        }
+#pragma unroll
+        for (int c = c0; c < c1; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            mx0 = fmaxf(mx0, __uint_as_float(sraw[c][i]));
+            mx1 = fmaxf(mx1, __uint_as_float(sraw[c][i + 1]));
+          }
+      };
+      mask_max(0, kFirst);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = kFirst; c < kChunks; ++c) regs_ready32(sraw[c]);
       tc_fence_before();
       __syncwarp();
       mbar_arrive_elect_addr(smem_u32(s_free));  // S_j is in registers: the next Q.K^T may overwrite it
-      if (valid < 64) {
-        // tail tile only (1370 = 10*128 + 90): keys beyond the sequence get -inf
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i >= valid) sraw[c][i] = 0xff800000u;
-      }
-      float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 2; ++c)
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          mx0 = fmaxf(mx0, __uint_as_float(sraw[c][i]));
-          mx1 = fmaxf(mx1, __uint_as_float(sraw[c][i + 1]));
-        }
-      // row maximum over both halves: exchange through shared memory (double buffered by parity)
-      const uint32_t xm = xmax_addr + uint32_t((j & 1) * 2 * kTile) * 4u;
-      TRACE(half, j, 2, __float_as_uint(fmaxf(mx0, mx1)));
-      sts_f32(xm + uint32_t(half * kTile + row) * 4u, fmaxf(mx0, mx1));
-      pair_sync(quad);
-      TRACE(half, j, 3, 0);
-      const float mx = fmaxf(fmaxf(mx0, mx1), lds_f32(xm + uint32_t((half ^ 1) * kTile + row) * 4u));
-      const float m_new = fmaxf(m_used, mx * p.scale_log2);
+      mask_max(kFirst, kChunks);
+      TRACE(0, j, 2, __float_as_uint(fmaxf(mx0, mx1)));
+      const float m_new = fmaxf(m_used, fmaxf(mx0, mx1) * p.scale_log2);
       // lazy max: keep the stale max while it is within 2^8 of the true one
       const bool bump = (m_new - m_used) > 8.0f;
       float alpha = 1.0f;
@@ -292,42 +303,48 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
         m_used = m_new;
       }
       float2 sum2 = make_float2(0.0f, 0.0f);
-      uint32_t pk[32];
       const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
       const float2 nm2 = make_float2(-m_used, -m_used);
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < kChunks; ++c) {
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           const float2 x = __ffma2_rn(make_float2(__uint_as_float(sraw[c][i]), __uint_as_float(sraw[c][i + 1])), sc2, nm2);
           const float2 e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
           sum2 = __fadd2_rn(sum2, e);
-          pk[c * 16 + (i >> 1)] = pack_bf16x2(e.x, e.y);
+          // packed bf16 pairs are written over score registers already consumed (pair k of the row lands in
+          // word k: chunk c fills the lower / upper half of chunk c / 2), so P is stored from aligned 32-register
+          // blocks without a second array
+          sraw[c >> 1][(c & 1) * 16 + (i >> 1)] = pack_bf16x2(e.x, e.y);
         }
-        if (c == 0) {
+        if (c == kChunks / 2 - 1) {
           if (j > 0) o_ready = mbar_test_wait(o_full, (j - 1) & 1);
           if (j + 1 < n_kv) s_ready = mbar_test_wait(s_full, (j + 1) & 1);
         }
       }
       l = l * alpha + (sum2.x + sum2.y);
-      TRACE(half, j, 4, pk[31] ^ pk[15] ^ __float_as_uint(l));
+      TRACE(0, j, 4, sraw[0][31] ^ sraw[0][15] ^ __float_as_uint(l));
 
       if (j > 0) {
         if (!o_ready) mbar_wait(o_full, (j - 1) & 1);  // P.V of the previous tile retired
         tc_fence_after();
-        TRACE(half, j, 5, 0);
+        TRACE(0, j, 5, 0);
         if (__any_sync(0xffffffffu, bump)) {
-          // rescale this thread's half of the running O row (rare after the first tiles)
-          uint32_t o[32];
-          tmem_ld_32x32(t_lane + kColO + half * 32, o);
-          tmem_ld_wait();
+          // rescale the running O row (rare after the first tiles)
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st_32x32(t_lane + kColO + half * 32, o);
+          for (int oc = 0; oc < kD / 32; ++oc) {
+            uint32_t o[32];
+            tmem_ld_32x32(t_lane + kColO + oc * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32(t_lane + kColO + oc * 32, o);
+          }
         }
       }
-      tmem_st_32x32(t_lane + kColP + half * 32, pk);
-      TRACE(half, j, 6, 0);
+#pragma unroll
+      for (int c = 0; c < kChunks / 2; ++c) tmem_st_32x32(t_lane + kColP + c * 32, sraw[c]);
+      TRACE(0, j, 6, 0);
     }
     tmem_st_wait();
     tc_fence_before();
@@ -335,30 +352,30 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
     mbar_arrive_elect_addr(smem_u32(p_full));  // P of the last tile
 
     // ---- epilogue: O / l -> ctx ----
-    xsum[half * kTile + row] = l;
-    pair_sync(quad);
-    const float l_row = l + xsum[(half ^ 1) * kTile + row];
-    const float inv_l = 1.0f / l_row;
+    const float inv_l = 1.0f / l;
     mbar_wait(o_full, (n_kv - 1) & 1);
     tc_fence_after();
     const int q_row = q_tile * kTile + row;
     // log-sum-exp of the scaled scores in the log2 domain (m_used is the possibly stale maximum the
     // probabilities were formed against, so m_used + log2(sum) is exact): saved for dod_fmha_bwd
-    if (p.lse != nullptr && half == 0 && q_row < p.seq)
-      p.lse[(int64_t(b) * p.heads + head) * p.seq + q_row] = m_used + log2f(l_row);
-    __nv_bfloat16* dst = p.ctx + (int64_t(b) * p.seq + q_row) * p.ldo + head * kD + half * 32;
-    uint32_t o[32];
-    tmem_ld_32x32(t_lane + kColO + half * 32, o);
-    tmem_ld_wait();
-    if (q_row < p.seq) {
+    if (p.lse != nullptr && q_row < p.seq)
+      p.lse[(int64_t(b) * p.heads + head) * p.seq + q_row] = m_used + log2f(l);
+    __nv_bfloat16* dst = p.ctx + (int64_t(b) * p.seq + q_row) * p.ldo + head * kD;
 #pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        uint4 v;
-        v.x = pack_bf16x2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
-        v.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
-        v.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
-        v.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
-        *reinterpret_cast<uint4*>(dst + i) = v;
+    for (int oc = 0; oc < kD / 32; ++oc) {
+      uint32_t o[32];
+      tmem_ld_32x32(t_lane + kColO + oc * 32, o);
+      tmem_ld_wait();
+      if (q_row < p.seq) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+          v.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+          v.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+          v.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(dst + oc * 32 + i) = v;
+        }
       }
     }
   }
