@@ -133,26 +133,42 @@ class LLinear:
         t = ops.gemm(x, self.a, None)                         # x A^T  [M, 64]
         return ops.gemm(x, self.w, self.bias, a2=t, w2=self.b, **kw), t
 
-    def bwd(self, dy, x, t, grads, *, need_dx=True):
+    def bwd(self, dy, x, t, grads, *, need_dx=True, splits=None):
+        """splits: number of equal row slices (images) of the M-reduction.  With it the two LoRA weight gradients
+        run as batched tcgen05 GEMMs (ops.lowrank_wgrad_tc: each operand read once, only the diagonal blocks of
+        fused q / k / v); without it, or for ranks / part sizes the GEMM form does not cover, dod_lowrank_wgrad."""
         dev = dy.device
         dt = ops.gemm(dy, self.bT, None)                      # alpha * dy B   [M, 64]
-        db = grads.buf(("lb", id(self)), (self.n, self.r), dev)
-        ops.lowrank_wgrad(dy, t, self.r, db, transposed=False)                 # dy^T (x A^T)
         da = grads.buf(("la", id(self)), (self.r, self.k), dev)
-        ops.lowrank_wgrad(x, dt, self.r, da, transposed=True)                  # (alpha dy B)^T x
+        nb, rp = len(self.r_parts), self.r_parts[0]
+        tc = (splits is not None and dy.shape[0] % splits == 0 and self.r % 8 == 0 and rp % 8 == 0 and
+              self.n % nb == 0 and all(r == rp for r in self.r_parts) and
+              all(m.out_features == self.n // nb for m in self.mods) and self.k % 8 == 0 and (self.n // nb) % 8 == 0)
+        if tc:
+            dbc = grads.buf(("lbc", id(self)), (nb, self.n // nb, rp), dev)
+            ops.lowrank_wgrad_tc(dy, t, rp, dbc, transposed=False, splits=splits, blocks=nb)   # dy^T (x A^T), per part
+            ops.lowrank_wgrad_tc(x, dt, self.r, da, transposed=True, splits=splits)            # (alpha dy B)^T x
+        else:
+            db = grads.buf(("lb", id(self)), (self.n, self.r), dev)
+            ops.lowrank_wgrad(dy, t, self.r, db, transposed=False)
+            ops.lowrank_wgrad(x, dt, self.r, da, transposed=True)
         if not need_dx:
             return None
         return ops.gemm(dy, self.wT, None, a2=dt, w2=self.aT)                  # dy W + dt A
 
     def collect(self, grads, out):
         db, da = grads.bufs.get(("lb", id(self))), grads.bufs.get(("la", id(self)))
-        if db is None:
+        dbc = grads.bufs.get(("lbc", id(self)))          # per-part [parts, n, r] (tensor-core form)
+        if db is None and dbc is None:
             return
         r0 = n0 = 0
-        for m, r in zip(self.mods, self.r_parts):
+        for i, (m, r) in enumerate(zip(self.mods, self.r_parts)):
             n = m.out_features
             # d/dB of alpha * B (A x) = alpha * dy^T t ; b_full carries alpha -> dt does, db does not
-            out[id(m.lora_B.weight)] = db[n0:n0 + n, r0:r0 + r] * float(m.alpha)
+            g_b = dbc[i] if dbc is not None else db[n0:n0 + n, r0:r0 + r]
+            if dbc is not None and db is not None:
+                g_b = g_b + db[n0:n0 + n, r0:r0 + r]
+            out[id(m.lora_B.weight)] = g_b * float(m.alpha)
             out[id(m.lora_A.weight)] = da[r0:r0 + r]
             r0 += r
             n0 += n
@@ -246,20 +262,20 @@ class EncTrainLayer:
     def bwd(self, dx_out, sv, b, n, heads, grads, need_dx_in):
         d = dx_out.shape[1]
         dy = ops.eltwise(ops.ELT_SCALE_COLS, dx_out, vec=self.ls2, out_dtype=BF16)
-        da = self.fc2.bwd(dy, sv["a"], sv["t4"], grads)
+        da = self.fc2.bwd(dy, sv["a"], sv["t4"], grads, splits=b)
         if self.swiglu:
             dz = ops.eltwise(ops.ELT_SWIGLU_BWD, da, sv["z"], cols=da.shape[1])
         else:
             dz = ops.eltwise(ops.ELT_GELU_BWD, da, sv["z"])
-        dh2 = self.fc1.bwd(dz, sv["h2"], sv["t3"], grads)
+        dh2 = self.fc1.bwd(dz, sv["h2"], sv["t3"], grads, splits=b)
         dx_mid = ops.layernorm_bwd(dh2, sv["x_mid"], self.n2[0], 1e-6, dres=dx_out)
         dy = ops.eltwise(ops.ELT_SCALE_COLS, dx_mid, vec=self.ls1, out_dtype=BF16)
-        dctx = self.proj.bwd(dy, sv["ctx"], sv["t2"], grads)
+        dctx = self.proj.bwd(dy, sv["ctx"], sv["t2"], grads, splits=b)
         dqkv = torch.empty_like(sv["qkv"])
         # fused flash-style backward: probabilities recomputed from q, k and the saved log-sum-exp
         ops.fmha_bwd(sv["qkv"], sv["ctx"], dctx, sv["lse"], dqkv, b, n, heads, q_off=0, k_off=d, v_off=2 * d,
                      scale=0.125)
-        dh1 = self.qkv.bwd(dqkv, sv["h1"], sv["t1"], grads, need_dx=need_dx_in)
+        dh1 = self.qkv.bwd(dqkv, sv["h1"], sv["t1"], grads, need_dx=need_dx_in, splits=b)
         if not need_dx_in:
             return None
         return ops.layernorm_bwd(dh1, sv["x"], self.n1[0], 1e-6, dres=dx_mid)

@@ -427,6 +427,37 @@ def lowrank_wgrad(big, small, r, out, *, transposed, alpha=1.0):
     return out
 
 
+def lowrank_wgrad_tc(big, small, r, out, *, transposed, splits, blocks=1, scratch=None):
+    """The LoRA weight gradients on the tensor cores: per diagonal block i < blocks (fused q / k / v projections)
+
+        out[i, c, j] += sum_m big[m, i * cb + c] * small[m, i * r + j]        (transposed: out[i, j, c])
+
+    as ONE batched M-reduction GEMM: the rows are cut into `splits` equal slices (one per image), every
+    (slice, block) is a batch entry whose operands are read as stored (MN-major tcgen05 tiles, a_trans / w_trans),
+    the fp32 partial products [splits, blocks, ...] meet in one column-sum pass.  `big` is read from HBM exactly
+    once (dod_lowrank_wgrad re-read it for every eight LoRA columns and computed the off-diagonal blocks too).
+    big bf16 [M, blocks * cb], small bf16 [M, >= blocks * r] (unit inner stride), r % 8 == 0, M % splits == 0,
+    out f32 contiguous [blocks, cb, r] (or [blocks, r, cb])."""
+    assert big.dtype == torch.bfloat16 and small.dtype == torch.bfloat16 and out.dtype == torch.float32
+    m, cols = big.shape
+    assert cols % blocks == 0 and m % splits == 0 and r % 8 == 0 and small.shape[1] >= blocks * r
+    cb, mc = cols // blocks, m // splits
+    ldb, lds = _rowmajor(big, "big"), _rowmajor(small, "small")
+    b4 = big.as_strided((splits, blocks, mc, cb), (mc * ldb, cb, ldb, 1), big.storage_offset())
+    s4 = small.as_strided((splits, blocks, mc, r), (mc * lds, r, lds, 1), small.storage_offset())
+    shape = (splits, blocks, r, cb) if transposed else (splits, blocks, cb, r)
+    assert out.is_contiguous() and out.numel() == blocks * cb * r
+    if scratch is None or scratch.numel() < splits * blocks * cb * r:
+        scratch = torch.empty(splits * blocks * cb * r, dtype=torch.float32, device=big.device)
+    part = scratch[:splits * blocks * cb * r].view(shape)
+    if transposed:
+        gemm_batched(s4, b4, part, a_trans=True, w_trans=True)
+    else:
+        gemm_batched(b4, s4, part, a_trans=True, w_trans=True)
+    colsum(part.view(splits, blocks * cb * r), out.view(-1))
+    return out
+
+
 def colsum(x, out):
     """out[c] += sum_m x[m, c] (f32 accumulate)."""
     m, cols = x.shape

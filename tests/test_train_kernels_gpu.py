@@ -173,6 +173,26 @@ def test_lowrank_wgrad_and_colsum(ops, r, c):
     assert _rel(cs, big.float().sum(0)) < 1e-4
 
 
+@pytest.mark.parametrize("splits,mc,blocks,cb,r", [(4, 1370, 1, 1024, 8), (3, 257, 3, 384, 8), (2, 1370, 3, 1024, 8),
+                                                   (5, 100, 1, 4096, 8), (2, 640, 1, 768, 24), (1, 300, 2, 256, 16)])
+def test_lowrank_wgrad_tc(ops, splits, mc, blocks, cb, r):
+    """LoRA dA / dB as one batched M-reduction tcgen05 GEMM over per-image row slices and diagonal blocks
+    (fused q / k / v), against fp32 torch on the same bf16 operands; accumulates into `out`."""
+    g = _g(splits * 1000 + mc + blocks)
+    m = splits * mc
+    big = _randn((m, blocks * cb), g).bfloat16()
+    small = torch.zeros((m, 64), dtype=torch.bfloat16, device="cuda")
+    small[:, :blocks * r] = _randn((m, blocks * r), g).bfloat16()
+    ref = torch.stack([big[:, i * cb:(i + 1) * cb].float().t() @ small[:, i * r:(i + 1) * r].float()
+                       for i in range(blocks)])                                   # [blocks, cb, r]
+    out = torch.ones((blocks, cb, r), device="cuda")
+    ops.lowrank_wgrad_tc(big, small, r, out, transposed=False, splits=splits, blocks=blocks)
+    assert _rel(out - 1.0, ref) < 1e-4
+    out_t = torch.zeros((blocks, r, cb), device="cuda")
+    ops.lowrank_wgrad_tc(big, small, r, out_t, transposed=True, splits=splits, blocks=blocks)
+    assert _rel(out_t, ref.transpose(1, 2)) < 1e-4
+
+
 @pytest.mark.parametrize("d", [256, 768, 1024])
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 def test_layernorm_bwd(ops, d, dt):
