@@ -566,6 +566,21 @@ def measure_train(cx, steps, warmup, batch=32, parity_images=2):
                          collective="one NCCL all-reduce of the flat fp32 gradient per step + the 1-float num_boxes "
                                     "SUM, inside the timed step" if cx.world > 1 else "none at N=1",
                          loss=float(step().detach()))
+    if os.environ.get("DOD_BENCH_GRAPH", "1") != "0":
+        # the same step replayed from ONE CUDA graph (runtime.GraphedTrainStep: forward, GPU matcher, fused criterion,
+        # backward, the NCCL all-reduces, clip + Adam; targets re-staged from the host every step): what the ~700
+        # launch gaps of the eager step cost
+        try:
+            from dino_detector.runtime import GraphedTrainStep
+            tg_host = make_targets(batch, seed=400 + cx.rank)
+            gstep = GraphedTrainStep(model, crit, opt, x, max_targets=max(t["labels"].numel() for t in tg_host) + 1)
+            gms, _ = cx.timed(lambda: gstep(x, tg_host), steps, warmup)
+            rec["graph"] = {"ms_per_step": gms / steps, "value": batch * cx.world * steps / (gms * 1e-3), "unit": UNIT,
+                            "loss": float(sum(gstep(x, tg_host).values())),
+                            "what": "the same train step as ONE CUDA graph replay per step (NCCL all-reduces captured)"}
+            del gstep
+        except Exception as e:                                   # never take the bench line down
+            rec["graph"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
     del model, opt, x
     torch.cuda.empty_cache()
     return rec, parity
