@@ -21,6 +21,13 @@
 // prologue / epilogue of each CTA.  profiles/r01_summary.md and r02_summary.md hold the measured phase
 // timelines and the variants that were tried and dropped (polynomial exp2 offload, 3 CTAs per SM,
 // two query tiles per CTA, a persistent software-pipelined single-stream kernel).
+// Round 2, measured on top of it and dropped (profiles/r02_summary.md): a persistent form of this kernel (two
+// CTAs per SM walking the (image, head, query tile) items: 588 us -- the co-resident CTA already fills the
+// prologue / epilogue of its neighbour), skipping the warps whose rows lie beyond the sequence (563 us) and the
+// exp2 of key chunks beyond it (617 us: the branch splits the MUFU block), reducing the row maximum on the side
+// and applying it one tile late (644 / 685 us).  ncu: XU pipe 62 %, issue slots 41 %, stall reasons wait /
+// long scoreboard -- the in-order chain of two independently phased softmax warps per scheduler is the bound.
+// fmha64_kernel at the end of this file (64-key tiles, four CTAs per SM) is the opt-in form for short sequences.
 // Optionally writes the per-row log-sum-exp consumed by dod_fmha_bwd.
 //
 // Replaces F.scaled_dot_product_attention behind HF Dinov2SelfAttention
@@ -389,6 +396,238 @@ fmha_kernel(const __grid_constant__ CUtensorMap tm_qkv, const FmhaParams p) {
 }
 
 
+
+// ---------------------------------------------------------------------------------------------------------
+// fmha64_kernel: the same pass with 64-key tiles and FOUR CTAs per SM.
+//
+// The 128-key kernel above is bound by the in-order chain of its softmax warps, not by a pipe (ncu: XU 62 %,
+// issue slots 41 %, two independently phased softmax warps per scheduler; removing 2-5 % of the exp2 work
+// does not move it, adding 64 ALU instructions per tile costs 15 %).  Here a thread still owns a query row
+// but only 64 score columns at a time (~90 registers), P is written over the consumed S columns in TMEM
+// (128 TMEM columns per CTA: S / P 64 + O 64) and ONE thread issues loads and both MMAs, so four CTAs
+// (4 x 160 threads, 4 x 48 KB smem, 4 x 128 TMEM columns) are resident and every scheduler has four
+// independently phased softmax warps feeding the XU pipe.  S_{j+1} is issued right behind P.V_j by the same
+// thread (tcgen05.mma executes in issue order, so it cannot overwrite P_j before P.V_j has read it); the
+// bubble this leaves in one CTA's chain is covered by the other three.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kKV = 64;                       // keys per tile
+constexpr int kKVBytes = kKV * kD * 2;        // 8 KB
+constexpr int kThreads64 = kSoftmaxThreads + 32;
+constexpr uint32_t kTmemCols64 = 128;
+constexpr uint32_t kColS64 = 0, kColO64 = 64;  // P (bf16, 32 columns) is written over S
+constexpr int kSmemBytes64 = kTileBytes + 2 * kKVStages * kKVBytes + 256 + 1024;
+
+__global__ void __launch_bounds__(kThreads64, 4)
+fmha64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const FmhaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kTileBytes;
+  uint8_t* sV = sK + kKVStages * kKVBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kKVStages * kKVBytes);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;   // [2]
+  uint64_t* k_empty = bars + 3;  // [2]
+  uint64_t* v_full = bars + 5;   // [2]
+  uint64_t* v_empty = bars + 7;  // [2]
+  uint64_t* s_full = bars + 9;
+  uint64_t* p_full = bars + 10;
+  uint64_t* o_full = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q_tile = blockIdx.x;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int n_kv = (p.seq + kKV - 1) / kKV;
+  constexpr int kIssueWarp = kSoftmaxThreads / 32;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tm_q);
+    prefetch_tmap(&tm_kv);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kKVStages; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, kSoftmaxThreads / 32);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == kIssueWarp) tmem_alloc<kTmemCols64>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == kIssueWarp) {
+    if (lane == 0) {
+      // ---------------- loads + both MMAs (single thread) ----------------
+      constexpr uint32_t idesc_s = make_idesc_bf16(kTile, kKV, false, false);  // Q.K^T
+      constexpr uint32_t idesc_o = make_idesc_bf16(kTile, kD, false, true);    // P.V (V MN-major)
+      const int qc = p.q_off + head * kD, kc = p.k_off + head * kD, vc = p.v_off + head * kD;
+      mbar_expect_tx(q_full, kTileBytes);
+      tma_load_3d(sQ, &tm_q, q_full, qc, q_tile * kTile, b);
+      for (int j = 0; j < kKVStages && j < n_kv; ++j) {
+        mbar_expect_tx(&k_full[j], kKVBytes);
+        tma_load_3d(sK + j * kKVBytes, &tm_kv, &k_full[j], kc, j * kKV, b);
+      }
+      for (int j = 0; j < kKVStages && j < n_kv; ++j) {
+        mbar_expect_tx(&v_full[j], kKVBytes);
+        tma_load_3d(sV + j * kKVBytes, &tm_kv, &v_full[j], vc, j * kKV, b);
+      }
+      const uint64_t dq = make_sdesc_sw128(smem_u32(sQ), 16, 1024);
+      auto issue_s = [&](int j) {
+        const int s = j % kKVStages;
+        mbar_wait(&k_full[s], (j / kKVStages) & 1);
+        tc_fence_after();
+        const uint64_t dk = make_sdesc_sw128(smem_u32(sK + s * kKVBytes), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k)
+          umma_ss(tmem + kColS64, dq + uint64_t(2 * k), dk + uint64_t(2 * k), idesc_s, k != 0);
+        umma_commit(s_full);
+        umma_commit(&k_empty[s]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < n_kv; ++j) {
+        const int s = j % kKVStages;
+        mbar_wait(&v_full[s], (j / kKVStages) & 1);
+        mbar_wait(p_full, j & 1);  // P_j stored over S_j (and O rescaled if needed)
+        tc_fence_after();
+        {
+          const uint32_t sv = smem_u32(sV + s * kKVBytes);
+#pragma unroll
+          for (int k = 0; k < kKV / 16; ++k) {
+            const uint64_t dv = make_sdesc_sw128(sv + k * 16 * 128, 16, 1024);
+            umma_ts(tmem + kColO64, tmem + kColS64 + 8 * k, dv, idesc_o, (j | k) != 0);
+          }
+        }
+        umma_commit(o_full);
+        umma_commit(&v_empty[s]);
+        // the next scores go over P_j: issued behind P.V_j, executed behind it
+        if (j + 1 < n_kv) issue_s(j + 1);
+        if (j + kKVStages < n_kv) {
+          // K_j retired before s_full(j) fired; V_j retires with P.V_j
+          mbar_wait(&k_empty[s], (j / kKVStages) & 1);
+          mbar_expect_tx(&k_full[s], kKVBytes);
+          tma_load_3d(sK + s * kKVBytes, &tm_kv, &k_full[s], kc, (j + kKVStages) * kKV, b);
+          mbar_wait(&v_empty[s], (j / kKVStages) & 1);
+          mbar_expect_tx(&v_full[s], kKVBytes);
+          tma_load_3d(sV + s * kKVBytes, &tm_kv, &v_full[s], vc, (j + kKVStages) * kKV, b);
+        }
+      }
+    }
+  } else {
+    // ---------------- softmax warps: one thread per query row, 64 keys per tile ----------------
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const uint32_t t_lane = tmem + (uint32_t(quad * 32) << 16);
+    const uint32_t a_s_full = smem_u32(s_full), a_p_full = smem_u32(p_full), a_o_full = smem_u32(o_full);
+    float m_used = -INFINITY;  // in log2 units (already scaled)
+    float l = 0.0f;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait_addr(a_s_full, j & 1);
+      tc_fence_after();
+      const int valid = p.seq - j * kKV;
+      uint32_t sraw[2][32];
+      tmem_ld_32x32(t_lane + kColS64, sraw[0]);
+      tmem_ld_32x32(t_lane + kColS64 + 32, sraw[1]);
+      tmem_ld_wait();
+      if (valid < kKV) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= valid) sraw[c][i] = 0xff800000u;
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          mx0 = fmaxf(mx0, __uint_as_float(sraw[c][i]));
+          mx1 = fmaxf(mx1, __uint_as_float(sraw[c][i + 1]));
+        }
+      const float m_new = fmaxf(m_used, fmaxf(mx0, mx1) * p.scale_log2);
+      const bool bump = (m_new - m_used) > 8.0f;  // lazy maximum, as in the 128-key kernel
+      float alpha = 1.0f;
+      if (bump) {
+        alpha = exp2f(m_used - m_new);
+        m_used = m_new;
+      }
+      float2 sum2 = make_float2(0.0f, 0.0f);
+      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+      const float2 nm2 = make_float2(-m_used, -m_used);
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(sraw[c][i]), __uint_as_float(sraw[c][i + 1])), sc2, nm2);
+          const float2 e = make_float2(ex2_approx(x.x), ex2_approx(x.y));
+          sum2 = __fadd2_rn(sum2, e);
+          sraw[0][c * 16 + (i >> 1)] = pack_bf16x2(e.x, e.y);  // pair k of the row -> word k (already consumed)
+        }
+      l = l * alpha + (sum2.x + sum2.y);
+      if (j > 0 && __any_sync(0xffffffffu, bump)) {
+        mbar_wait_addr(a_o_full, (j - 1) & 1);  // P.V_{j-1} retired (it precedes S_j in the pipe: no real wait)
+        tc_fence_after();
+#pragma unroll
+        for (int oc = 0; oc < kD / 32; ++oc) {
+          uint32_t o[32];
+          tmem_ld_32x32(t_lane + kColO64 + oc * 32, o);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_32x32(t_lane + kColO64 + oc * 32, o);
+        }
+      }
+      tmem_st_32x32(t_lane + kColS64, sraw[0]);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      mbar_arrive_elect_addr(a_p_full);
+    }
+    // ---- epilogue: O / l -> ctx ----
+    const float inv_l = 1.0f / l;
+    mbar_wait_addr(a_o_full, (n_kv - 1) & 1);
+    tc_fence_after();
+    const int q_row = q_tile * kTile + row;
+    if (p.lse != nullptr && q_row < p.seq)
+      p.lse[(int64_t(b) * p.heads + head) * p.seq + q_row] = m_used + log2f(l);
+    __nv_bfloat16* dst = p.ctx + (int64_t(b) * p.seq + q_row) * p.ldo + head * kD;
+#pragma unroll
+    for (int oc = 0; oc < kD / 32; ++oc) {
+      uint32_t o[32];
+      tmem_ld_32x32(t_lane + kColO64 + oc * 32, o);
+      tmem_ld_wait();
+      if (q_row < p.seq) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+          v.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+          v.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+          v.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(dst + oc * 32 + i) = v;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kIssueWarp) {
+    tc_fence_after();
+    tmem_dealloc<kTmemCols64>(tmem);
+  }
+}
+
 }  // namespace
 }  // namespace dod
 
@@ -430,6 +669,25 @@ extern "C" int32_t dod_fmha_fwd(const dod_fmha_args* a, dod_stream_t stream_) {
   p.ldo = a->ldo;
   p.lse = a->lse;
   dim3 grid((a->seq + kTile - 1) / kTile, a->heads, a->batch);
+  // DOD_FMHA64=1 selects the 4-CTA/SM 64-key kernel: faster on short sequences (64 x 12 heads: 21.5 vs 28.1 us at
+  // 100 tokens, 59 vs 69 us at 257), level from ~384 tokens, slower at 1370 (590 vs 559 us).  It is opt-in: the
+  // recorded parity margins (profiles/r02_parity_margins.json) belong to the 128-key kernel, and the 3-block g/14
+  // case with its degenerate (1, 257) sampling grid sits within 10 % of the 2e-2 bar with either kernel.
+  const char* e64 = getenv("DOD_FMHA64");
+  const bool use64 = e64 != nullptr && e64[0] == '1';
+  if (use64) {
+    static PerDeviceOnce attr64_once;
+    if (attr64_once.first()) {
+      DOD_CUDA_OK(cudaFuncSetAttribute(fmha64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes64));
+    }
+    CUtensorMap tm_kv;
+    if (int rc = make_tmap_3d(&tm_kv, a->qkv, 2, a->batch, a->seq, a->ld, a->seq * a->ld, a->ld, kKV, kD))
+      return rc;
+    fmha64_kernel<<<grid, kThreads64, kSmemBytes64, stream>>>(tm, tm_kv, p);
+    int rc = check_cuda(cudaGetLastError(), "fmha64_kernel launch");
+    if (rc == 0) count_launch();
+    return rc;
+  }
   fmha_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tm, p);
   int rc = check_cuda(cudaGetLastError(), "fmha_kernel launch");
   if (rc == 0) count_launch();

@@ -345,8 +345,13 @@ def test_patchify_and_pos_resize(ops):
 
 
 # ----------------------------------------------------------------------- attention
-@pytest.mark.parametrize("b,s,h", [(1, 128, 1), (2, 257, 6), (1, 1370, 12), (3, 100, 2), (2, 384, 3)])
-def test_fmha(ops, b, s, h):
+@pytest.mark.parametrize("kernel", ["128-key tiles, 2 CTAs/SM", "64-key tiles, 4 CTAs/SM"])
+@pytest.mark.parametrize("b,s,h", [(1, 128, 1), (2, 257, 6), (1, 1370, 12), (3, 100, 2), (2, 384, 3), (5, 65, 2),
+                                   (2, 1, 1)])
+def test_fmha(ops, b, s, h, kernel, monkeypatch):
+    """Both forward kernels (default: 128-key tiles; DOD_FMHA64=1: 64-key tiles, four CTAs per SM) on every
+    shape, log-sum-exp output included."""
+    monkeypatch.setenv("DOD_FMHA64", "1" if kernel.startswith("64") else "0")
     g = _gen(s + h)
     d = h * 64
     qkv = _randn((b * s, 3 * d), g).bfloat16()
@@ -356,6 +361,11 @@ def test_fmha(ops, b, s, h):
     ref = ref.permute(0, 2, 1, 3).reshape(b * s, d)
     assert _rel(out, ref) < 2e-2
     assert (out.float() - ref).abs().max().item() < 2e-2
+    lse = torch.empty((b, h, s), dtype=torch.float32, device="cuda")
+    out2 = ops.fmha(qkv, b, s, h, q_off=0, k_off=d, v_off=2 * d, scale=0.125, lse=lse)
+    assert torch.equal(out, out2)
+    want = torch.logsumexp(q @ k.transpose(-1, -2) * 0.125, dim=-1) * 1.4426950408889634       # log2 domain
+    assert (lse - want).abs().max().item() < 2e-3 * max(1.0, want.abs().max().item())
 
 
 def test_fmha_bench_shape_full_size(ops):
