@@ -1107,7 +1107,12 @@ int launch2(const dod_gemm_args& a, cudaStream_t stream) {
   fill_ln_params(p, a);
   p.w_shared = w_shared ? 1 : 0;
   const int tiles = p.tiles_m * p.tiles_n * p.batch;
-  const int pairs = tiles < num_sms() / 2 ? tiles : num_sms() / 2;
+  int max_pairs = num_sms() / 2;
+  if (const char* e = getenv("DOD_GEMM_MAX_PAIRS")) {  // developer knob: how the mainloop scales with fewer SMs
+    const int v = atoi(e);
+    if (v > 0 && v < max_pairs) max_pairs = v;
+  }
+  const int pairs = tiles < max_pairs ? tiles : max_pairs;
   gemm2_kernel<RES, TRANS><<<2 * pairs, kThreads, L::kTotal, stream>>>(tm_a, tm_w, tm_a2, tm_w2, tm_out, tm_res,
                                                                        tm_out2, p);
   return check_cuda(cudaGetLastError(), "gemm2_kernel launch");
