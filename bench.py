@@ -684,9 +684,9 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         try:
-            rate, times = reference_forward_rate(REF_SAMPLE_IMAGES, 4, 1, threads)
+            rate, times = reference_forward_rate(REF_SAMPLE_IMAGES, 12, 1, threads)
             cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "reference",
-                   "sample": f"{REF_SAMPLE_IMAGES} of {BATCH} images per forward, 4 timed forwards of the unmodified "
+                   "sample": f"{REF_SAMPLE_IMAGES} of {BATCH} images per forward, {len(times)} timed forwards of the unmodified "
                              f"reference detector (baseline/_ref, default ctor, fp32, eval, no_grad), median "
                              f"{statistics.median(times):.2f} s, total {sum(times):.1f} s"}
         except Exception as e:
