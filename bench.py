@@ -500,7 +500,8 @@ def measure_train(cx, steps, warmup, batch=32, parity_images=2):
         sum(crit(model(xs[cx.rank]), ts[cx.rank]).values()).backward()
         sync.all_reduce(average=True)
         got = sync.flat.clone()
-        crit.sync_num_boxes = False                  # single-process evaluation of the whole batch
+        crit.sync_num_boxes = False                  # single-process evaluation of the whole batch:
+        sync.early = False                           # no collective from inside its backward either
         x_all, t_all = torch.cat(xs), [t for tt in ts for t in tt]
 
         def single():
@@ -511,6 +512,7 @@ def measure_train(cx, steps, warmup, batch=32, parity_images=2):
         want = single()
         again = single()                             # the same computation twice: what atomics alone move
         crit.sync_num_boxes = True
+        sync.early = True
         names = {id(p): n for n, p in model.named_parameters()}
 
         def per_tensor(a_flat, b_flat):
@@ -563,8 +565,11 @@ def measure_train(cx, steps, warmup, batch=32, parity_images=2):
     rec = cx.rate_record(batch * cx.world, ms, steps, gf, warmup_steps=warmup, model="facebook/dinov2-large",
                          lora_r=8, decoder="deformable (reference default)", dropout=0.1,
                          trainable_params=sync.numel, grad_allreduce_bytes=sync.numel * 4,
-                         collective="one NCCL all-reduce of the flat fp32 gradient per step + the 1-float num_boxes "
-                                    "SUM, inside the timed step" if cx.world > 1 else "none at N=1",
+                         collective="one NCCL all-reduce of the flat fp32 gradient per step + the 1-float num_boxes SUM, "
+                                    "inside the timed step" + (" (DOD_EARLY_ALLREDUCE=1: projection + decoder part on a side "
+                                                               "stream under the LoRA blocks' backward)"
+                                                               if os.environ.get("DOD_EARLY_ALLREDUCE") == "1" else "")
+                                    if cx.world > 1 else "none at N=1",
                          loss=float(step().detach()))
     if os.environ.get("DOD_BENCH_GRAPH", "1") != "0":
         # the same step replayed from ONE CUDA graph (runtime.GraphedTrainStep: forward, GPU matcher, fused criterion,

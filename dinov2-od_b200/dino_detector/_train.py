@@ -594,13 +594,7 @@ def train_backward(model, st, dlogits, dboxes):
     if st.proj is not None:
         dmem = st.proj.bwd(dmem, st.lnf_out, grads)
     dx = ops.layernorm_bwd(dmem, st.x_final, st.fln[0], 1e-6)
-    # ---- LoRA blocks ----
-    for j in reversed(range(len(st.enc))):
-        lt, sv = st.enc[j]
-        dx = lt.bwd(dx, sv, b, n, st.heads, grads, need_dx_in=(j > 0))
-    # ---- collect ----
-    for lt, _ in st.enc:
-        lt.collect(grads, out)
+    # ---- projection / decoder / head gradients are complete: collect them now ----
     if st.proj is not None:
         st.proj.collect(grads, out)
     seen = set()
@@ -612,7 +606,23 @@ def train_backward(model, st, dlogits, dboxes):
             m.collect(grads, out)
     for m in (st.cls, st.box0, st.box1):
         m.collect(grads, out)
+    # parallel.FlatGradSync (one flat fp32 gradient buffer): this part of the buffer is all-reduced on a
+    # side stream UNDER the backward of the LoRA blocks below; the node then returns None for these parameters
+    from . import parallel
+    sink = parallel.sink_for(dec.query_embed.weight)
+    in_place = sink.early_tail(out) if sink is not None and sink.early_enabled() else set()
+    # ---- LoRA blocks ----
+    for j in reversed(range(len(st.enc))):
+        lt, sv = st.enc[j]
+        dx = lt.bwd(dx, sv, b, n, st.heads, grads, need_dx_in=(j > 0))
+    for lt, _ in st.enc:
+        lt.collect(grads, out)
+    for pid in in_place:
+        out[pid] = _IN_PLACE
     return out
+
+
+_IN_PLACE = object()     # marker: the gradient was accumulated into p.grad from inside the backward
 
 
 class _DetectorFn(torch.autograd.Function):
@@ -639,6 +649,9 @@ class _DetectorFn(torch.autograd.Function):
         outs = []
         for pid, shape, dt in zip(ctx.param_ids, ctx.param_shapes, ctx.param_dtypes):
             t = g.get(pid)
+            if t is _IN_PLACE:
+                outs.append(None)
+                continue
             # every parameter handed to this node gets a gradient (DDP waits for each hook)
             outs.append(torch.zeros(shape, dtype=dt, device=dev) if t is None
                         else t.reshape(shape).to(dt).contiguous())

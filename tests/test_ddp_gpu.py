@@ -26,6 +26,9 @@ def _loss(out):
 
 def _worker(rank, world, port, results, use_ddp):
     import sys
+    if use_ddp == "flat-early":
+        os.environ["DOD_EARLY_ALLREDUCE"] = "1"      # projection + decoder part all-reduced from inside the backward
+        use_ddp = False
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from helpers import build_product_model, synth
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -44,6 +47,8 @@ def _worker(rank, world, port, results, use_ddp):
         sync = FlatGradSync(model.parameters())
         sync.zero()
         _loss(model(x[rank:rank + 1].cuda())).backward()
+        if os.environ.get("DOD_EARLY_ALLREDUCE") == "1":
+            assert sync._early is not None and sync._early[1] > 0, "the early all-reduce did not start in the backward"
         sync.all_reduce(average=True)
     torch.cuda.synchronize()
     if rank == 0:
@@ -64,7 +69,7 @@ def _worker(rank, world, port, results, use_ddp):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("use_ddp", [True, False])
+@pytest.mark.parametrize("use_ddp", [True, False, "flat-early"])
 def test_two_gpu_gradient_allreduce_matches_single_process(use_ddp):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
