@@ -633,7 +633,7 @@ def run_ours(args):
         k = max(2, min(args.steps, 8))
         records["infer_l14"] = measure_inference(cx, "facebook/dinov2-large", 64, 64, k, 3, "large")
         per_gpu = max(32, 512 // cx.world)
-        records["infer_c5"] = measure_inference(cx, "facebook/dinov2-giant", per_gpu, 32, 2 if per_gpu > 128 else 3,
+        records["infer_c5"] = measure_inference(cx, "facebook/dinov2-giant", per_gpu, 64, 2 if per_gpu > 128 else 3,
                                                 1 if per_gpu > 128 else 2, "giant")
         records["infer_c5"]["global_batch"] = per_gpu * cx.world
         rec, parity = measure_train(cx, k, 3)
