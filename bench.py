@@ -20,7 +20,7 @@ deformable decoder, 50 queries), bf16 compute with fp32 accumulation, 64 synthet
   records   the other BASELINE.json configs, measured at this N in the same run (each: images/s of the whole job,
             ms/step, model-level TFLOP/s and its fraction of the sustained / burst bf16 peak):
               infer_l14   L/14 detector inference, 64 images per GPU          (north_star's target model)
-              infer_c5    g/14 detector inference, global batch 512 split 512/N per GPU, micro-batches of 32
+              infer_c5    g/14 detector inference, global batch 512 split 512/N per GPU, micro-batches of 64
               train_c4    L/14 LoRA r=8 + deformable decoder FULL train step (forward, GPU matcher, fused
                           criterion, hand-written backward, ONE NCCL all-reduce of the flat gradient inside the
                           timed step, global-norm clip + Adam), 32 images per GPU
