@@ -78,8 +78,14 @@ class FlatGradSync:
         and, if those parameters are exactly a suffix of the buffer, start its all-reduce (AVG) on the side stream.
         Returns the set of parameter ids whose gradient is now in place (the autograd node returns None for them)."""
         idx = sorted(self._offsets[pid][0] for pid in grads_by_id if pid in self._offsets)
-        if not idx or idx != list(range(idx[0], len(self.params))) or self._early is not None:
+        if not idx or idx != list(range(idx[0], len(self.params))):
             return set()
+        if self._early is not None:
+            # a second backward before all_reduce() (gradient accumulation): the tail holds the AVERAGE of the first
+            # micro-step already; adding this micro-step's local gradients and averaging again is exact, because an
+            # average is the same on every rank.  The additions must follow the collective that is still in flight.
+            torch.cuda.current_stream(self.flat.device).wait_event(self._early[0])
+            self._early = None
         done = set()
         for pid, g in grads_by_id.items():
             ent = self._offsets.get(pid)

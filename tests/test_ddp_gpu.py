@@ -26,8 +26,10 @@ def _loss(out):
 
 def _worker(rank, world, port, results, use_ddp):
     import sys
-    if use_ddp == "flat-early":
+    micro = 1
+    if use_ddp in ("flat-early", "flat-early-accum"):
         os.environ["DOD_EARLY_ALLREDUCE"] = "1"      # projection + decoder part all-reduced from inside the backward
+        micro = 2 if use_ddp == "flat-early-accum" else 1     # two backward passes before the optimizer's all-reduce
         use_ddp = False
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from helpers import build_product_model, synth
@@ -37,7 +39,7 @@ def _worker(rank, world, port, results, use_ddp):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     model, sd, kw = build_product_model("c1_small_std", device=f"cuda:{rank}", dropout=0.0)
     model.train()
-    x = synth.make_images(world, 224, 224, seed=21)
+    x = synth.make_images(world * micro, 224, 224, seed=21)
     if use_ddp:
         from torch.nn.parallel import DistributedDataParallel as DDP
         ddp = DDP(model, device_ids=[rank], find_unused_parameters=True)      # reference train.py:677
@@ -46,7 +48,9 @@ def _worker(rank, world, port, results, use_ddp):
         from dino_detector.parallel import FlatGradSync
         sync = FlatGradSync(model.parameters())
         sync.zero()
-        _loss(model(x[rank:rank + 1].cuda())).backward()
+        for k in range(micro):
+            i = k * world + rank
+            _loss(model(x[i:i + 1].cuda())).backward()
         if os.environ.get("DOD_EARLY_ALLREDUCE") == "1":
             assert sync._early is not None and sync._early[1] > 0, "the early all-reduce did not start in the backward"
         sync.all_reduce(average=True)
@@ -69,7 +73,7 @@ def _worker(rank, world, port, results, use_ddp):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("use_ddp", [True, False, "flat-early"])
+@pytest.mark.parametrize("use_ddp", [True, False, "flat-early", "flat-early-accum"])
 def test_two_gpu_gradient_allreduce_matches_single_process(use_ddp):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
