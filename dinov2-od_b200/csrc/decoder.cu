@@ -314,6 +314,83 @@ __global__ void deform_sample_kernel(const TV* __restrict__ value, const float* 
   }
 }
 
+// Vectorised form for bf16 values: a thread owns EIGHT adjacent channels of one (image, query) row (one 16-byte
+// gather per corner), so the per-head scalars -- softmax over the points, clamped sampling position, corner
+// indices and weights -- are evaluated once per eight channels instead of once per channel, and several rows
+// share a CTA.  The per-channel arithmetic (products, order of the four corner terms and of the points) is the
+// one of deform_sample_kernel: results are bit-identical (tests/test_kernels_gpu.py).
+template <typename TO>
+__global__ void __launch_bounds__(256)
+deform_sample_vec_kernel(const __nv_bfloat16* __restrict__ value, const float* __restrict__ ref,
+                         const float* __restrict__ offs, const float* __restrict__ logits, TO* __restrict__ out,
+                         int64_t rows, int queries, int heads, int points, int dh, int gh, int gw, int64_t ldv,
+                         int64_t ldref, int64_t ldoffs, int64_t ldlog, int64_t ldo, int ref_is_logit) {
+  const int groups = heads * dh / 8;                       // 8-channel groups per row
+  const int rows_per_cta = blockDim.x / groups;
+  const int r_in = threadIdx.x / groups;
+  if (r_in >= rows_per_cta) return;
+  const int64_t row = int64_t(blockIdx.x) * rows_per_cta + r_in;
+  if (row >= rows) return;
+  const int c = (threadIdx.x - r_in * groups) * 8;
+  const int b = int(row / queries);
+  const int64_t hw = int64_t(gh) * gw;
+  float rx = ref[row * ldref + 0], ry = ref[row * ldref + 1];
+  if (ref_is_logit) {
+    rx = 1.0f / (1.0f + expf(-rx));
+    ry = 1.0f / (1.0f + expf(-ry));
+  }
+  const int h = c / dh;
+  const float* lg = logits + row * ldlog + h * points;
+  const float* of = offs + row * ldoffs + h * points * 2;
+  float mx = -INFINITY;
+  for (int p = 0; p < points; ++p) mx = fmaxf(mx, lg[p]);
+  float den = 0.f;
+  for (int p = 0; p < points; ++p) den += expf(lg[p] - mx);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int p = 0; p < points; ++p) {
+    const float wgt = expf(lg[p] - mx) / den;
+    const float lx = fminf(fmaxf(rx + of[2 * p + 0], 0.f), 1.f);
+    const float ly = fminf(fmaxf(ry + of[2 * p + 1], 0.f), 1.f);
+    const float sx = lx * float(gw - 1), sy = ly * float(gh - 1);
+    int x0 = int(floorf(sx)), y0 = int(floorf(sy));
+    int x1 = x0 + 1, y1 = y0 + 1;
+    x0 = min(max(x0, 0), gw - 1);
+    x1 = min(max(x1, 0), gw - 1);
+    y0 = min(max(y0, 0), gh - 1);
+    y1 = min(max(y1, 0), gh - 1);
+    const float wx1 = sx - float(x0), wx0 = 1.0f - wx1;
+    const float wy1 = sy - float(y0), wy0 = 1.0f - wy1;
+    const float w00 = __fmul_rn(wx0, wy0), w01 = __fmul_rn(wx0, wy1), w10 = __fmul_rn(wx1, wy0),
+                w11 = __fmul_rn(wx1, wy1);
+    const __nv_bfloat16* vb = value + int64_t(b) * hw * ldv + c;
+    const uint4 q00 = __ldg(reinterpret_cast<const uint4*>(vb + (int64_t(y0) * gw + x0) * ldv));
+    const uint4 q01 = __ldg(reinterpret_cast<const uint4*>(vb + (int64_t(y1) * gw + x0) * ldv));
+    const uint4 q10 = __ldg(reinterpret_cast<const uint4*>(vb + (int64_t(y0) * gw + x1) * ldv));
+    const uint4 q11 = __ldg(reinterpret_cast<const uint4*>(vb + (int64_t(y1) * gw + x1) * ldv));
+    const uint32_t a00[4] = {q00.x, q00.y, q00.z, q00.w}, a01[4] = {q01.x, q01.y, q01.z, q01.w};
+    const uint32_t a10[4] = {q10.x, q10.y, q10.z, q10.w}, a11[4] = {q11.x, q11.y, q11.z, q11.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int w = i >> 1;
+      const bool hi = i & 1;
+      const float v00 = __uint_as_float(hi ? (a00[w] & 0xffff0000u) : (a00[w] << 16));
+      const float v01 = __uint_as_float(hi ? (a01[w] & 0xffff0000u) : (a01[w] << 16));
+      const float v10 = __uint_as_float(hi ? (a10[w] & 0xffff0000u) : (a10[w] << 16));
+      const float v11 = __uint_as_float(hi ? (a11[w] & 0xffff0000u) : (a11[w] << 16));
+      float s = __fmul_rn(v00, w00);
+      s = __fadd_rn(s, __fmul_rn(v01, w01));
+      s = __fadd_rn(s, __fmul_rn(v10, w10));
+      s = __fadd_rn(s, __fmul_rn(v11, w11));
+      acc[i] = __fadd_rn(acc[i], __fmul_rn(s, wgt));
+    }
+  }
+  TO* op = out + row * ldo + c;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) st1(op + i, acc[i]);
+}
+
 // ---------------------------------------------------------------------------
 // row utilities
 // ---------------------------------------------------------------------------
@@ -449,6 +526,30 @@ extern "C" int32_t dod_deform_sample(const dod_deform_sample_args* a, dod_stream
   const int d_model = int(a->heads * a->head_dim);
   const int threads = d_model >= 1024 ? 1024 : ((d_model + 31) / 32) * 32;
   const unsigned grid = unsigned(a->batch * a->queries);
+  {
+    // vectorised kernel: bf16 values, 8-channel groups inside one head, 16-byte-aligned value rows
+    const char* e_vec = getenv("DOD_DEFORM_VEC");  // 0: the thread-per-channel kernel (A/B, bit-equality test)
+    const bool no_vec = e_vec != nullptr && e_vec[0] == '0';
+    const int groups = d_model / 8;
+    if (!no_vec && a->value_dtype == DOD_BF16 && a->head_dim % 8 == 0 && a->ldv % 8 == 0 &&
+        (reinterpret_cast<uintptr_t>(a->value) & 15) == 0 && groups >= 1 && groups <= 256) {
+      const int rows_per_cta = 256 / groups;
+      const int64_t rows = a->batch * a->queries;
+      const unsigned vgrid = unsigned((rows + rows_per_cta - 1) / rows_per_cta);
+      const int vthreads = rows_per_cta * groups;
+#define DOD_LAUNCH_DSV(TO)                                                                                  \
+  deform_sample_vec_kernel<TO><<<vgrid, vthreads, 0, stream>>>(                                             \
+      (const __nv_bfloat16*)a->value, a->ref, a->offs, a->logits, (TO*)a->out, rows, int(a->queries),       \
+      int(a->heads), int(a->points), int(a->head_dim), int(a->grid_h), int(a->grid_w), a->ldv, a->ldref,    \
+      a->ldoffs, a->ldlog, a->ldo, a->ref_is_logit)
+      if (a->out_dtype == DOD_BF16) DOD_LAUNCH_DSV(__nv_bfloat16);
+      else DOD_LAUNCH_DSV(float);
+#undef DOD_LAUNCH_DSV
+      int rc = check_cuda(cudaGetLastError(), "deform_sample_vec_kernel launch");
+      if (rc == 0) count_launch();
+      return rc;
+    }
+  }
 #define DOD_LAUNCH_DS(TV, TO)                                                                      \
   deform_sample_kernel<TV, TO><<<grid, threads, 0, stream>>>(                                      \
       (const TV*)a->value, a->ref, a->offs, a->logits, (TO*)a->out, int(a->queries), int(a->heads), \

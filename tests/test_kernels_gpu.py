@@ -458,6 +458,25 @@ def test_deform_sample(ops, gh, gw):
     assert _rel(out16, ref) < 2e-2
 
 
+@pytest.mark.parametrize("b,q,h,p,dh,gh,gw", [(2, 50, 8, 2, 96, 10, 137), (3, 100, 4, 4, 64, 1, 257), (64, 50, 8, 2, 96, 10, 137),
+                                             (1, 7, 8, 2, 32, 16, 16)])
+def test_deform_sample_vectorised_is_bit_identical(ops, b, q, h, p, dh, gh, gw, monkeypatch):
+    """The 8-channels-per-thread kernel (bf16 values) against the thread-per-channel kernel: same bits, both
+    output types, value rows taken as a column slice of a wider buffer (ldv > d_model) like in the decoder."""
+    g = _gen(b + q + dh)
+    d = h * dh
+    wide = _randn((b * gh * gw, d + 64), g).bfloat16()
+    value = wide[:, 32:32 + d]
+    raw = _randn((b * q, 3 * h * p + 8), g)
+    args = (value, raw[:, 3 * h * p:3 * h * p + 2], raw[:, :2 * h * p], raw[:, 2 * h * p:3 * h * p], b, q, h, p, dh, gh, gw)
+    for odt in (torch.bfloat16, torch.float32):
+        monkeypatch.setenv("DOD_DEFORM_VEC", "0")
+        want = ops.deform_sample(*args, ref_is_logit=True, out_dtype=odt)
+        monkeypatch.setenv("DOD_DEFORM_VEC", "1")
+        got = ops.deform_sample(*args, ref_is_logit=True, out_dtype=odt)
+        assert torch.equal(got, want)
+
+
 def test_row_utils(ops):
     g = _gen(1)
     x = _randn((77, 96), g)
