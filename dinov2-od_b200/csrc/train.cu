@@ -625,6 +625,176 @@ __global__ void __launch_bounds__(512) deform_sample_bwd_kernel(const void* __re
   }
 }
 
+
+// Vectorised form for bf16 values: a thread owns EIGHT adjacent channels of one (image, query) row (one 16-byte
+// gather per corner, the per-head scalars evaluated once per group), d value leaves as two 16-byte vector
+// reductions per corner (red.global.add.v4.f32) instead of eight scalar atomics, and the per-(head, point)
+// sums for d weight / d location are formed WITHOUT atomics: every thread sums its eight channels in order,
+// writes the partial to shared memory, and one thread per (row, head, point) adds the head's dh / 8 partials in
+// order.  The gradients of the position projections (sums of large cancelling terms) are therefore the same
+// bits on every run -- the thread-per-channel kernel above adds 96 channels per head through shared-memory
+// atomics in arrival order.
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+deform_sample_bwd_vec_kernel(const __nv_bfloat16* __restrict__ value, const float* __restrict__ ref,
+                             const float* __restrict__ offs, const float* __restrict__ logits,
+                             const void* __restrict__ dout, int do_dt, float* __restrict__ dvalue,
+                             float* __restrict__ dq, int64_t rows, int queries, int heads, int points, int dh, int gh,
+                             int gw, int64_t ldv_, int64_t ldref, int64_t ldoffs, int64_t ldlog, int64_t lddo,
+                             int64_t lddv, int64_t lddq, int ref_is_logit) {
+  extern __shared__ float sh[];
+  const int groups = heads * dh / 8, gph = dh / 8;  // 8-channel groups per row / per head
+  const int hp = heads * points;
+  const int rows_per_cta = blockDim.x / groups;
+  float* s_part = sh;                                         // [rows_per_cta][groups][points][3]
+  float* s_dw = s_part + rows_per_cta * groups * points * 3;  // [rows_per_cta][hp]
+  float* s_dl = s_dw + rows_per_cta * hp;                     // [rows_per_cta][hp][2]
+  const int r_in = threadIdx.x / groups;
+  const int grp = threadIdx.x - r_in * groups;
+  const int64_t row = int64_t(blockIdx.x) * rows_per_cta + r_in;
+  const bool live = r_in < rows_per_cta && row < rows;
+  float rx = 0.f, ry = 0.f;
+  if (live) {
+    rx = ref[row * ldref + 0];
+    ry = ref[row * ldref + 1];
+    if (ref_is_logit) {
+      rx = 1.0f / (1.0f + expf(-rx));
+      ry = 1.0f / (1.0f + expf(-ry));
+    }
+    const int c = grp * 8, h = c / dh;
+    const int b = int(row / queries);
+    const int64_t hw = int64_t(gh) * gw;
+    const float* lg = logits + row * ldlog + h * points;
+    const float* of = offs + row * ldoffs + h * points * 2;
+    float mx = -INFINITY;
+    for (int p = 0; p < points; ++p) mx = fmaxf(mx, lg[p]);
+    float den = 0.f;
+    for (int p = 0; p < points; ++p) den += expf(lg[p] - mx);
+    float g[8];
+    if (do_dt == DOD_F32) {
+      const float4 g0 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dout) + row * lddo + c);
+      const float4 g1 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dout) + row * lddo + c + 4);
+      g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+    } else {
+      const uint4 gq = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(dout) + row * lddo + c);
+      const uint32_t gwd[4] = {gq.x, gq.y, gq.z, gq.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        g[2 * i] = __uint_as_float(gwd[i] << 16);
+        g[2 * i + 1] = __uint_as_float(gwd[i] & 0xffff0000u);
+      }
+    }
+    for (int p = 0; p < points; ++p) {
+      const float wgt = expf(lg[p] - mx) / den;
+      const float ux = rx + of[2 * p + 0], uy = ry + of[2 * p + 1];
+      const float lx = fminf(fmaxf(ux, 0.f), 1.f), ly = fminf(fmaxf(uy, 0.f), 1.f);
+      const float sx = lx * float(gw - 1), sy = ly * float(gh - 1);
+      int x0 = int(floorf(sx)), y0 = int(floorf(sy));
+      int x1 = x0 + 1, y1 = y0 + 1;
+      x0 = min(max(x0, 0), gw - 1); x1 = min(max(x1, 0), gw - 1);
+      y0 = min(max(y0, 0), gh - 1); y1 = min(max(y1, 0), gh - 1);
+      const float wx1 = sx - float(x0), wx0 = 1.0f - wx1;
+      const float wy1 = sy - float(y0), wy0 = 1.0f - wy1;
+      const int64_t vb = int64_t(b) * hw;
+      const int64_t i00 = vb + int64_t(y0) * gw + x0, i01 = vb + int64_t(y1) * gw + x0;
+      const int64_t i10 = vb + int64_t(y0) * gw + x1, i11 = vb + int64_t(y1) * gw + x1;
+      const uint4 q00 = __ldg(reinterpret_cast<const uint4*>(value + i00 * ldv_ + c));
+      const uint4 q01 = __ldg(reinterpret_cast<const uint4*>(value + i01 * ldv_ + c));
+      const uint4 q10 = __ldg(reinterpret_cast<const uint4*>(value + i10 * ldv_ + c));
+      const uint4 q11 = __ldg(reinterpret_cast<const uint4*>(value + i11 * ldv_ + c));
+      const uint32_t a00[4] = {q00.x, q00.y, q00.z, q00.w}, a01[4] = {q01.x, q01.y, q01.z, q01.w};
+      const uint32_t a10[4] = {q10.x, q10.y, q10.z, q10.w}, a11[4] = {q11.x, q11.y, q11.z, q11.w};
+      // clamp(., 0, 1) passes the gradient only inside the closed interval (torch.clamp)
+      const float px = (ux >= 0.f && ux <= 1.f) ? float(gw - 1) : 0.f;
+      const float py = (uy >= 0.f && uy <= 1.f) ? float(gh - 1) : 0.f;
+      float d00[8], d01[8], d10[8], d11[8];
+      float dw = 0.f, dlx = 0.f, dly = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int w = i >> 1;
+        const bool hi = i & 1;
+        const float v00 = __uint_as_float(hi ? (a00[w] & 0xffff0000u) : (a00[w] << 16));
+        const float v01 = __uint_as_float(hi ? (a01[w] & 0xffff0000u) : (a01[w] << 16));
+        const float v10 = __uint_as_float(hi ? (a10[w] & 0xffff0000u) : (a10[w] << 16));
+        const float v11 = __uint_as_float(hi ? (a11[w] & 0xffff0000u) : (a11[w] << 16));
+        const float samp = v00 * (wx0 * wy0) + v01 * (wx0 * wy1) + v10 * (wx1 * wy0) + v11 * (wx1 * wy1);
+        const float gw_ = g[i] * wgt;
+        d00[i] = gw_ * wx0 * wy0;
+        d01[i] = gw_ * wx0 * wy1;
+        d10[i] = gw_ * wx1 * wy0;
+        d11[i] = gw_ * wx1 * wy1;
+        dw += g[i] * samp;
+        const float dsx = (v10 - v00) * wy0 + (v11 - v01) * wy1;
+        const float dsy = (v01 - v00) * wx0 + (v11 - v10) * wx1;
+        dlx += gw_ * dsx * px;
+        dly += gw_ * dsy * py;
+      }
+      float* o00 = dvalue + i00 * lddv + c;
+      float* o01 = dvalue + i01 * lddv + c;
+      float* o10 = dvalue + i10 * lddv + c;
+      float* o11 = dvalue + i11 * lddv + c;
+      red_add_v4(o00, d00[0], d00[1], d00[2], d00[3]); red_add_v4(o00 + 4, d00[4], d00[5], d00[6], d00[7]);
+      red_add_v4(o01, d01[0], d01[1], d01[2], d01[3]); red_add_v4(o01 + 4, d01[4], d01[5], d01[6], d01[7]);
+      red_add_v4(o10, d10[0], d10[1], d10[2], d10[3]); red_add_v4(o10 + 4, d10[4], d10[5], d10[6], d10[7]);
+      red_add_v4(o11, d11[0], d11[1], d11[2], d11[3]); red_add_v4(o11 + 4, d11[4], d11[5], d11[6], d11[7]);
+      float* sp = s_part + ((r_in * groups + grp) * points + p) * 3;
+      sp[0] = dw;
+      sp[1] = dlx;
+      sp[2] = dly;
+    }
+  }
+  __syncthreads();
+  // one thread per (row, head, point): the head's partials in group order
+  for (int i = threadIdx.x; i < rows_per_cta * hp; i += blockDim.x) {
+    const int r = i / hp, hpi = i - r * hp, h = hpi / points, p = hpi - h * points;
+    float dw = 0.f, dlx = 0.f, dly = 0.f;
+    for (int gi = 0; gi < gph; ++gi) {
+      const float* sp = s_part + ((r * groups + h * gph + gi) * points + p) * 3;
+      dw += sp[0];
+      dlx += sp[1];
+      dly += sp[2];
+    }
+    s_dw[r * hp + hpi] = dw;
+    s_dl[(r * hp + hpi) * 2 + 0] = dlx;
+    s_dl[(r * hp + hpi) * 2 + 1] = dly;
+  }
+  __syncthreads();
+  // softmax backward over the points, offsets (dq row layout = the fused query projection:
+  // [offsets 2hp | logits hp | ref 2]), then the reference point
+  for (int i = threadIdx.x; i < rows_per_cta * heads; i += blockDim.x) {
+    const int r = i / heads, h = i - r * heads;
+    const int64_t rw = int64_t(blockIdx.x) * rows_per_cta + r;
+    if (rw >= rows) continue;
+    const float* lg = logits + rw * ldlog + h * points;
+    const float* dwp = s_dw + r * hp + h * points;
+    float mx = -INFINITY;
+    for (int p = 0; p < points; ++p) mx = fmaxf(mx, lg[p]);
+    float den = 0.f;
+    for (int p = 0; p < points; ++p) den += expf(lg[p] - mx);
+    float dot = 0.f;
+    for (int p = 0; p < points; ++p) dot += expf(lg[p] - mx) / den * dwp[p];
+    for (int p = 0; p < points; ++p) {
+      const float w = expf(lg[p] - mx) / den;
+      dq[rw * lddq + 2 * hp + h * points + p] = w * (dwp[p] - dot);
+      dq[rw * lddq + (h * points + p) * 2 + 0] = s_dl[(r * hp + h * points + p) * 2 + 0];
+      dq[rw * lddq + (h * points + p) * 2 + 1] = s_dl[(r * hp + h * points + p) * 2 + 1];
+    }
+  }
+  for (int i = threadIdx.x; i < rows_per_cta * 2; i += blockDim.x) {
+    const int r = i >> 1, xy = i & 1;
+    const int64_t rw = int64_t(blockIdx.x) * rows_per_cta + r;
+    if (rw >= rows) continue;
+    float acc = 0.f;
+    for (int k = 0; k < hp; ++k) acc += s_dl[(r * hp + k) * 2 + xy];
+    float rr = ref[rw * ldref + xy];
+    if (ref_is_logit) rr = 1.0f / (1.0f + expf(-rr));
+    dq[rw * lddq + 3 * hp + xy] = ref_is_logit ? acc * rr * (1.0f - rr) : acc;
+  }
+}
+
 }  // namespace
 }  // namespace dod
 
@@ -790,6 +960,30 @@ extern "C" int32_t dod_deform_sample_bwd(const dod_deform_sample_bwd_args* a, do
   const int hp = int(a->heads * a->points);
   DOD_REQUIRE(a->lddq >= 3 * hp + 2, "dod_deform_sample_bwd: dqproj rows must hold 3*H*P + 2 columns");
   const int d_model = int(a->heads * a->head_dim);
+  {
+    // vectorised kernel: bf16 values, 8-channel groups inside one head, 16-byte-aligned rows of value / dout / dvalue
+    const char* e_vec = getenv("DOD_DEFORM_VEC");  // 0: the thread-per-channel kernel (A/B, tests)
+    const int groups = d_model / 8;
+    const bool do_f32 = a->dout_dtype == DOD_F32;
+    if (!(e_vec != nullptr && e_vec[0] == '0') && a->value_dtype == DOD_BF16 && a->head_dim % 8 == 0 &&
+        a->ldv % 8 == 0 && (reinterpret_cast<uintptr_t>(a->value) & 15) == 0 && a->lddv % 4 == 0 &&
+        (reinterpret_cast<uintptr_t>(a->dvalue) & 15) == 0 && a->lddo % (do_f32 ? 4 : 8) == 0 &&
+        (reinterpret_cast<uintptr_t>(a->dout) & 15) == 0 && groups >= 1 && groups <= 256) {
+      const int rows_per_cta = 256 / groups;
+      const int64_t rows = a->batch * a->queries;
+      const unsigned vgrid = unsigned((rows + rows_per_cta - 1) / rows_per_cta);
+      const size_t smem = size_t(rows_per_cta) * (size_t(groups) * a->points * 3 + 3 * hp) * sizeof(float);
+      if (smem <= 48 * 1024) {
+        deform_sample_bwd_vec_kernel<<<vgrid, rows_per_cta * groups, smem, stream>>>(
+            (const __nv_bfloat16*)a->value, a->ref, a->offs, a->logits, a->dout, a->dout_dtype, a->dvalue, a->dqproj,
+            rows, int(a->queries), int(a->heads), int(a->points), int(a->head_dim), int(a->grid_h), int(a->grid_w),
+            a->ldv, a->ldref, a->ldoffs, a->ldlog, a->lddo, a->lddv, a->lddq, a->ref_is_logit);
+        int rc = check_cuda(cudaGetLastError(), "deform_sample_bwd_vec_kernel launch");
+        if (rc == 0) count_launch();
+        return rc;
+      }
+    }
+  }
   const int threads = d_model >= 512 ? 512 : ((d_model + 31) / 32) * 32;
   deform_sample_bwd_kernel<<<unsigned(a->batch * a->queries), threads, 3 * hp * sizeof(float), stream>>>(
       a->value, a->value_dtype, a->ref, a->offs, a->logits, a->dout, a->dout_dtype, a->dvalue, a->dqproj,

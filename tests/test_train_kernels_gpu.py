@@ -275,6 +275,43 @@ def test_softmax_rows_fwd_bwd(ops):
     assert _rel(ds[:, :n], want) < 1e-2 and (ds[:, n:] == 0).all()
 
 
+@pytest.mark.parametrize("b,q,h,p,dh,gh,gw", [(2, 50, 8, 2, 96, 10, 137), (3, 33, 4, 4, 64, 1, 257), (32, 50, 8, 2, 96, 10, 137)])
+@pytest.mark.parametrize("do_dt", [torch.bfloat16, torch.float32])
+def test_deform_sample_bwd_vectorised(ops, b, q, h, p, dh, gh, gw, do_dt, monkeypatch):
+    """The 8-channels-per-thread backward (bf16 values: vector reductions into d value, atomics-free sums for the
+    position / weight gradients) against the thread-per-channel kernel and against torch autograd on the same
+    bf16-rounded values; its position gradients are the same bits on every run."""
+    from test_kernels_gpu import _deform_ref
+    g = _g(b * 7 + q + dh)
+    hp, d = h * p, h * dh
+    v16 = _randn((b * gh * gw, d), g).bfloat16()
+    cols = (3 * hp + 2 + 7) // 8 * 8
+    raw = torch.zeros((b * q, cols), device="cuda")
+    raw[:, :3 * hp + 2] = _randn((b * q, 3 * hp + 2), g) * 0.5
+    dout = _randn((b * q, d), g).to(do_dt)
+
+    def run(vec):
+        monkeypatch.setenv("DOD_DEFORM_VEC", vec)
+        dvalue = torch.zeros((b * gh * gw, d), device="cuda")
+        dq = torch.zeros((b * q, cols), device="cuda")
+        ops.deform_sample_bwd(v16, raw[:, 3 * hp:3 * hp + 2], raw[:, :2 * hp], raw[:, 2 * hp:3 * hp], dout, dvalue, dq,
+                              b, q, h, p, dh, gh, gw, ref_is_logit=True)
+        return dvalue, dq
+
+    dv_old, dq_old = run("0")
+    dv_new, dq_new = run("1")
+    assert _rel(dv_new, dv_old) < 1e-5
+    assert _rel(dq_new[:, :3 * hp + 2], dq_old[:, :3 * hp + 2]) < 1e-4
+    dv_again, dq_again = run("1")
+    assert torch.equal(dq_new, dq_again)                       # no atomics on this path
+    value = v16.float().requires_grad_(True)
+    rawg = raw.clone().requires_grad_(True)
+    out = _deform_ref(value, rawg[:, 3 * hp:3 * hp + 2].sigmoid(), rawg[:, :2 * hp], rawg[:, 2 * hp:3 * hp], b, q, h, p, dh, gh, gw)
+    out.backward(dout.float())
+    assert _rel(dv_new, value.grad) < 1e-4
+    assert _rel(dq_new[:, :3 * hp + 2], rawg.grad[:, :3 * hp + 2]) < 1e-3
+
+
 @pytest.mark.parametrize("gh,gw", [(10, 137), (1, 257)])
 def test_deform_sample_bwd_matches_autograd(ops, gh, gw):
     from test_kernels_gpu import _deform_ref
