@@ -181,7 +181,9 @@ DOD_API int32_t dod_pos_resize_bicubic(const dod_pos_resize_args* a, dod_stream_
 /* ---- fused multi-head self-attention (tcgen05, flash-style) --------------
  * ctx = softmax(Q K^T * scale) V per (batch, head); non-causal, no mask.
  * Replaces SDPA at modeling_dinov2.py:215-229.  q/k/v are column slices of one
- * fused projection buffer qkv[B*S, ld]: head h of q at columns q_off + h*64.  */
+ * fused projection buffer qkv[B*S, ld]: head h of q at columns q_off + h*64.
+ * Two kernels: 128-key tiles with two CTAs per SM (default), 64-key tiles with four CTAs per SM
+ * (environment DOD_FMHA64=1: faster below ~300 tokens); same contract, both tested on every shape.  */
 typedef struct {
   const void* qkv; /* bf16 [B*S, ld]                                          */
   void* ctx;       /* bf16 [B*S, ldo], head h at columns h*64                  */
@@ -374,7 +376,9 @@ DOD_API int32_t dod_softmax_bwd_rows(const dod_softmax_bwd_rows_args* a, dod_str
 
 /* Backward of dod_deform_sample.  dvalue (f32, [B*hw, lddv]) is accumulated with atomics and must
  * be zeroed by the caller; dqproj rows use the fused query-projection layout
- * [d offsets 2*H*P | d logits H*P | d reference logits 2].                                      */
+ * [d offsets 2*H*P | d logits H*P | d reference logits 2].  With bf16 values, head_dim % 8 == 0 and
+ * 16-byte-aligned rows the 8-channels-per-thread kernel runs: dvalue through vector reductions, dqproj
+ * from ordered sums (no atomics: identical bits on every run).                                      */
 typedef struct {
   const void* value; int32_t value_dtype;
   const float* ref; const float* offs; const float* logits;
