@@ -69,11 +69,27 @@ mha_tiny_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __res
                 T* __restrict__ out, int lq, int lk, int dh, int64_t ldq, int64_t ldk, int64_t ldv,
                 int64_t ldo, float scale) {
   extern __shared__ float sm[];
+  // VEC (bf16 inputs): K and V stay bf16 in shared memory (row pitch dh + 2 halves = an odd number of words,
+  // conflict-free for consecutive rows) and are widened on use -- the same fp32 values, so the same bits out --
+  // which takes the CTA from 68 to 49 KB at 50 x 50 x 96: four CTAs per SM instead of three, and the 512
+  // (image, head) problems of a 64-image batch fit ONE wave (592 slots) instead of 1.15 (56 -> ~35 us per layer).
+  constexpr bool K16 = VEC && sizeof(T) == 2;
   const int pitch = dh | 1, lkp = lk | 1;
+  const int pitch16 = dh + 2;      // halves
   float* sq = sm;                  // [lq][pitch]
-  float* sk = sq + lq * pitch;     // [lk][pitch]
-  float* sv = sk + lk * pitch;     // [lk][pitch]
-  float* sp = sv + lk * pitch;     // [lq][lkp]
+  float* sk = sq + lq * pitch;     // [lk][pitch] f32, or [lk][pitch16] bf16 followed by V in the same form
+  float* sv = K16 ? sk + (lk * pitch16 + 1) / 2 : sk + lk * pitch;
+  float* sp = K16 ? sv + (lk * pitch16 + 1) / 2 : sv + lk * pitch;  // [lq][lkp]
+  const uint16_t* sk16 = reinterpret_cast<const uint16_t*>(sk);
+  const uint16_t* sv16 = reinterpret_cast<const uint16_t*>(sv);
+  auto kval = [&](int r, int d) -> float {
+    if constexpr (K16) return __uint_as_float(uint32_t(sk16[r * pitch16 + d]) << 16);
+    else return sk[r * pitch + d];
+  };
+  auto vval = [&](int r, int d) -> float {
+    if constexpr (K16) return __uint_as_float(uint32_t(sv16[r * pitch16 + d]) << 16);
+    else return sv[r * pitch + d];
+  };
   const int h = blockIdx.x, b = blockIdx.y;
   const int t = threadIdx.x;
   if constexpr (VEC) {
@@ -87,13 +103,23 @@ mha_tiny_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __res
     }
     for (int i = t; i < lk * dv; i += kMhaThreads) {
       const int r = i / dv, c = (i - r * dv) << 3;
-      float x[8], y[8];
-      ld_row8<T, true>(k + (int64_t(b) * lk + r) * ldk + h * dh + c, x);
-      ld_row8<T, true>(v + (int64_t(b) * lk + r) * ldv + h * dh + c, y);
+      if constexpr (K16) {
+        // rows start word-aligned (pitch16 even), c is a multiple of 8: four 32-bit stores per operand
+        const uint4 kq = *reinterpret_cast<const uint4*>(k + (int64_t(b) * lk + r) * ldk + h * dh + c);
+        const uint4 vq = *reinterpret_cast<const uint4*>(v + (int64_t(b) * lk + r) * ldv + h * dh + c);
+        uint32_t* kd = reinterpret_cast<uint32_t*>(sk) + ((r * pitch16 + c) >> 1);
+        uint32_t* vd = reinterpret_cast<uint32_t*>(sv) + ((r * pitch16 + c) >> 1);
+        kd[0] = kq.x; kd[1] = kq.y; kd[2] = kq.z; kd[3] = kq.w;
+        vd[0] = vq.x; vd[1] = vq.y; vd[2] = vq.z; vd[3] = vq.w;
+      } else {
+        float x[8], y[8];
+        ld_row8<T, true>(k + (int64_t(b) * lk + r) * ldk + h * dh + c, x);
+        ld_row8<T, true>(v + (int64_t(b) * lk + r) * ldv + h * dh + c, y);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        sk[r * pitch + c + e] = x[e];
-        sv[r * pitch + c + e] = y[e];
+        for (int e = 0; e < 8; ++e) {
+          sk[r * pitch + c + e] = x[e];
+          sv[r * pitch + c + e] = y[e];
+        }
       }
     }
   } else {
@@ -118,11 +144,10 @@ mha_tiny_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __res
     const float* a1 = sq + min(q0 + 1, lq - 1) * pitch;
     const float* a2 = sq + min(q0 + 2, lq - 1) * pitch;
     const float* a3 = sq + min(q0 + 3, lq - 1) * pitch;
-    const float* c0 = sk + k0 * pitch;
-    const float* c1 = sk + min(k1, lk - 1) * pitch;
+    const int r0 = k0, r1 = min(k1, lk - 1);
     float acc[4][2] = {};
     for (int d = 0; d < dh; ++d) {
-      const float x0 = c0[d], x1 = c1[d];
+      const float x0 = kval(r0, d), x1 = kval(r1, d);
       const float y0 = a0[d], y1 = a1[d], y2 = a2[d], y3 = a3[d];
       acc[0][0] = fmaf(y0, x0, acc[0][0]); acc[0][1] = fmaf(y0, x1, acc[0][1]);
       acc[1][0] = fmaf(y1, x0, acc[1][0]); acc[1][1] = fmaf(y1, x1, acc[1][1]);
@@ -164,7 +189,7 @@ mha_tiny_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __res
     const float* p3 = sp + min(q0 + 3, lq - 1) * lkp;
     float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
     for (int j = 0; j < lk; ++j) {
-      const float x = sv[j * pitch + d];
+      const float x = vval(j, d);
       o0 = fmaf(p0[j], x, o0);
       o1 = fmaf(p1[j], x, o1);
       o2 = fmaf(p2[j], x, o2);
@@ -465,11 +490,13 @@ extern "C" int32_t dod_mha_small(const dod_mha_small_args* a, dod_stream_t strea
   DOD_REQUIRE(a->dtype == DOD_BF16 || a->dtype == DOD_F32, "dod_mha_small: bad dtype");
   if (a->lq <= 128 && a->lk <= 128) {
     const int pitch = int(a->head_dim) | 1, lkp = int(a->lk) | 1;
-    const size_t tiny = sizeof(float) * (size_t(a->lq + 2 * a->lk) * pitch + size_t(a->lq) * lkp);
+    const bool vec = a->dtype == DOD_BF16 && a->head_dim % 8 == 0 && a->ldq % 8 == 0 && a->ldk % 8 == 0 &&
+                     a->ldv % 8 == 0 && ((uintptr_t(a->q) | uintptr_t(a->k) | uintptr_t(a->v)) & 15) == 0;
+    // vec: K / V are kept as bf16 in shared memory (pitch head_dim + 2 halves), see mha_tiny_kernel
+    const size_t kv_words = vec ? 2 * ((size_t(a->lk) * (a->head_dim + 2) + 1) / 2) : size_t(2 * a->lk) * pitch;
+    const size_t tiny = sizeof(float) * (size_t(a->lq) * pitch + kv_words + size_t(a->lq) * lkp);
     if (tiny <= 200 * 1024) {
       dim3 grid(unsigned(a->heads), unsigned(a->batch));
-      const bool vec = a->dtype == DOD_BF16 && a->head_dim % 8 == 0 && a->ldq % 8 == 0 && a->ldk % 8 == 0 &&
-                       a->ldv % 8 == 0 && ((uintptr_t(a->q) | uintptr_t(a->k) | uintptr_t(a->v)) & 15) == 0;
 #define DOD_MHA_TINY(T, VEC)                                                                                    \
   {                                                                                                             \
     auto kern = mha_tiny_kernel<T, VEC>;                                                                        \

@@ -443,6 +443,24 @@ def _deform_ref(value, ref_pts, offs, logits, b, q, h, p, dh, gh, gw):
     return (samp * wts[..., None]).sum(3).reshape(b * q, h * dh)
 
 
+@pytest.mark.parametrize("b,l,h,dh", [(64, 50, 8, 96), (3, 100, 4, 64), (2, 128, 8, 32), (5, 7, 2, 192)])
+def test_query_self_attention_bf16_smem_form_is_bit_identical(ops, b, l, h, dh):
+    """mha_tiny_kernel keeps K / V as bf16 in shared memory when the rows are 16-byte aligned (four CTAs per SM);
+    rows that are not (ld % 8 != 0) take the fp32-staged form: same arithmetic, same bits, and both match fp32 torch."""
+    g = _gen(b + l + dh)
+    d = h * dh
+    vals = _randn((b * l, 3 * d), g).bfloat16()
+    outs = []
+    for pad in (8, 4):                                  # ld = 3d + 8: vector form; 3d + 4: scalar form
+        buf = torch.zeros((b * l, 3 * d + pad), dtype=torch.bfloat16, device="cuda")
+        buf[:, :3 * d] = vals
+        outs.append(ops.mha_small(buf[:, :d], buf[:, d:2 * d], buf[:, 2 * d:3 * d], b, l, l, h, dh, 1 / math.sqrt(dh)))
+    assert torch.equal(outs[0], outs[1])
+    q, k, v = (vals.float().view(b, l, 3, h, dh).permute(2, 0, 3, 1, 4))
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(b * l, d)
+    assert _rel(outs[0], ref) < 1e-2
+
+
 @pytest.mark.parametrize("gh,gw", [(10, 137), (1, 257), (16, 16)])
 def test_deform_sample(ops, gh, gw):
     g = _gen(gh)
